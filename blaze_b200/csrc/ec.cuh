@@ -1,0 +1,163 @@
+// Short-Weierstrass (a = 0) group law in extended-Jacobian ("XYZZ") coordinates.
+//
+//   affine (x, y)          <->  XYZZ (X, Y, ZZ, ZZZ) with x = X/ZZ, y = Y/ZZZ, ZZ^3 = ZZZ^2
+//   infinity               <->  ZZ == 0
+//   affine (0, 0)          is treated as the identity (padding record; not on any of the
+//                          three curves since b != 0)
+//
+// Formulas: EFD "xyzz" for short Weierstrass curves -- madd-2008-s (8M+2S), add-2008-s
+// (12M+2S), dbl-2008-s-1 (6M+4S+...); a = 0 for BLS12-377, BLS12-381 and BN254.
+// All three operations are COMPLETE here: equal inputs fall through to doubling, opposite
+// inputs give infinity.  The reference's own test vectors need this: tiling a 256-element
+// block (tests/msm/mod.rs:92-109 of the reference) puts thousands of copies of one point in
+// a single bucket.
+#pragma once
+#include "ff.cuh"
+
+namespace bz {
+
+template <class C>
+struct Affine {
+  Fe<typename C::Fq> x, y;   // Montgomery form
+};
+
+template <class C>
+struct XYZZ {
+  Fe<typename C::Fq> X, Y, ZZ, ZZZ;   // Montgomery form
+};
+
+template <class C>
+struct ec {
+  typedef typename C::Fq Fq;
+  typedef ff<Fq> F;
+  typedef Fe<Fq> E;
+  typedef Affine<C> A;
+  typedef XYZZ<C> P;
+
+  BZ_HDI static P infinity() {
+    P r;
+    r.X = F::zero(); r.Y = F::zero(); r.ZZ = F::zero(); r.ZZZ = F::zero();
+    return r;
+  }
+  BZ_HDI static bool is_inf(const P& p) { return F::is_zero(p.ZZ); }
+  BZ_HDI static bool is_identity(const A& a) { return F::is_zero(a.x) && F::is_zero(a.y); }
+
+  BZ_HDI static P from_affine(const A& a) {
+    if (is_identity(a)) return infinity();
+    P r;
+    r.X = a.x; r.Y = a.y; r.ZZ = F::one(); r.ZZZ = F::one();
+    return r;
+  }
+
+  // 2*(x, y) for an affine point (mdbl-2008-s-1)
+  BZ_HDI static P dbl_affine(const A& a) {
+    P r;
+    E U = F::dbl(a.y);
+    E V = F::sqr(U);
+    E W = F::mul(U, V);
+    E S = F::mul(a.x, V);
+    E x2 = F::sqr(a.x);
+    E M = F::add(F::dbl(x2), x2);
+    r.X = F::sub(F::sqr(M), F::dbl(S));
+    r.Y = F::sub(F::mul(M, F::sub(S, r.X)), F::mul(W, a.y));
+    r.ZZ = V;
+    r.ZZZ = W;
+    return r;   // y == 0 gives ZZ = 0 = infinity (2-torsion), consistent
+  }
+
+  BZ_HDI static P dbl(const P& p) {
+    if (is_inf(p)) return p;
+    P r;
+    E U = F::dbl(p.Y);
+    E V = F::sqr(U);
+    E W = F::mul(U, V);
+    E S = F::mul(p.X, V);
+    E x2 = F::sqr(p.X);
+    E M = F::add(F::dbl(x2), x2);
+    r.X = F::sub(F::sqr(M), F::dbl(S));
+    r.Y = F::sub(F::mul(M, F::sub(S, r.X)), F::mul(W, p.Y));
+    r.ZZ = F::mul(V, p.ZZ);
+    r.ZZZ = F::mul(W, p.ZZZ);
+    return r;
+  }
+
+  // acc += a   (mixed addition, complete)
+  BZ_HDI static void madd(P& acc, const A& a) {
+    if (is_identity(a)) return;
+    if (is_inf(acc)) {
+      acc.X = a.x; acc.Y = a.y; acc.ZZ = F::one(); acc.ZZZ = F::one();
+      return;
+    }
+    E Pd = F::sub(F::mul(a.x, acc.ZZ), acc.X);    // U2 - X1
+    E Rd = F::sub(F::mul(a.y, acc.ZZZ), acc.Y);   // S2 - Y1
+    if (F::is_zero(Pd)) {
+      if (F::is_zero(Rd)) acc = dbl_affine(a);
+      else acc = infinity();
+      return;
+    }
+    E PP = F::sqr(Pd);
+    E PPP = F::mul(Pd, PP);
+    E Q = F::mul(acc.X, PP);
+    E X3 = F::sub(F::sub(F::sqr(Rd), PPP), F::dbl(Q));
+    E Y3 = F::sub(F::mul(Rd, F::sub(Q, X3)), F::mul(acc.Y, PPP));
+    acc.ZZ = F::mul(acc.ZZ, PP);
+    acc.ZZZ = F::mul(acc.ZZZ, PPP);
+    acc.X = X3;
+    acc.Y = Y3;
+  }
+
+  // acc += b   (full addition, complete)
+  BZ_HDI static void add(P& acc, const P& b) {
+    if (is_inf(b)) return;
+    if (is_inf(acc)) { acc = b; return; }
+    E U1 = F::mul(acc.X, b.ZZ);
+    E U2 = F::mul(b.X, acc.ZZ);
+    E S1 = F::mul(acc.Y, b.ZZZ);
+    E S2 = F::mul(b.Y, acc.ZZZ);
+    E Pd = F::sub(U2, U1);
+    E Rd = F::sub(S2, S1);
+    if (F::is_zero(Pd)) {
+      if (F::is_zero(Rd)) acc = dbl(acc);
+      else acc = infinity();
+      return;
+    }
+    E PP = F::sqr(Pd);
+    E PPP = F::mul(Pd, PP);
+    E Q = F::mul(U1, PP);
+    E X3 = F::sub(F::sub(F::sqr(Rd), PPP), F::dbl(Q));
+    E Y3 = F::sub(F::mul(Rd, F::sub(Q, X3)), F::mul(S1, PPP));
+    acc.ZZ = F::mul(F::mul(acc.ZZ, b.ZZ), PP);
+    acc.ZZZ = F::mul(F::mul(acc.ZZZ, b.ZZZ), PPP);
+    acc.X = X3;
+    acc.Y = Y3;
+  }
+
+  BZ_HDI static A neg(const A& a) {
+    A r;
+    r.x = a.x;
+    r.y = F::neg(a.y);
+    return r;
+  }
+
+  // k * p for a small non-negative k (double-and-add, MSB first)
+  BZ_HDI static P mul_small(const P& p, uint32_t k) {
+    P r = infinity();
+    for (int bit = 31; bit >= 0; bit--) {
+      r = dbl(r);
+      if ((k >> bit) & 1) add(r, p);
+    }
+    return r;
+  }
+
+  // XYZZ -> affine (Montgomery form); returns false for infinity
+  BZ_HDI static bool to_affine(const P& p, A& out) {
+    if (is_inf(p)) return false;
+    // x = X/ZZ, y = Y/ZZZ; 1/ZZZ = t, 1/ZZ = t^2 * ZZZ... use one inversion of ZZZ*ZZ
+    E zi = F::inv(F::mul(p.ZZ, p.ZZZ));           // 1/(ZZ*ZZZ)
+    out.x = F::mul(p.X, F::mul(zi, p.ZZZ));       // X/ZZ
+    out.y = F::mul(p.Y, F::mul(zi, p.ZZ));        // Y/ZZZ
+    return true;
+  }
+};
+
+}  // namespace bz
