@@ -62,6 +62,21 @@ BZ_DI uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) {
 BZ_DI uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) {
   uint32_t r; asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r;
 }
+BZ_DI uint64_t mul_wide(uint32_t a, uint32_t b) {
+  uint64_t r; asm("mul.wide.u32 %0, %1, %2;" : "=l"(r) : "r"(a), "r"(b)); return r;
+}
+BZ_DI uint64_t mad_wide(uint32_t a, uint32_t b, uint64_t c) {
+  uint64_t r; asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(c)); return r;
+}
+BZ_DI uint64_t add_cc64(uint64_t a, uint64_t b) {
+  uint64_t r; asm volatile("add.cc.u64 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
+}
+BZ_DI uint64_t addc_cc64(uint64_t a, uint64_t b) {
+  uint64_t r; asm volatile("addc.cc.u64 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
+}
+BZ_DI uint64_t addc64(uint64_t a, uint64_t b) {
+  uint64_t r; asm volatile("addc.u64 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
+}
 #else
 // ---- host emulation (test vehicle) ----
 inline uint32_t& flag() { static thread_local uint32_t f = 0; return f; }
@@ -88,6 +103,16 @@ inline uint32_t mad_hi_cc(uint32_t a, uint32_t b, uint32_t c) { return add3(mul_
 inline uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { return add3(mul_lo(a, b), c, flag(), true); }
 inline uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { return add3(mul_hi(a, b), c, flag(), true); }
 inline uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { return add3(mul_hi(a, b), c, flag(), false); }
+inline uint64_t mul_wide(uint32_t a, uint32_t b) { return (uint64_t)a * b; }
+inline uint64_t mad_wide(uint32_t a, uint32_t b, uint64_t c) { return (uint64_t)a * b + c; }
+inline uint64_t add3_64(uint64_t a, uint64_t b, uint32_t cin, bool set) {
+  unsigned __int128 t = (unsigned __int128)a + b + cin;
+  if (set) flag() = (uint32_t)(t >> 64);
+  return (uint64_t)t;
+}
+inline uint64_t add_cc64(uint64_t a, uint64_t b) { return add3_64(a, b, 0, true); }
+inline uint64_t addc_cc64(uint64_t a, uint64_t b) { return add3_64(a, b, flag(), true); }
+inline uint64_t addc64(uint64_t a, uint64_t b) { return add3_64(a, b, flag(), false); }
 #endif
 
 }  // namespace cc

@@ -1,0 +1,804 @@
+// Host side of libblaze_b200.so: the C ABI declared in include/blaze_b200.h, the DriverClient
+// device arena, and the MSMClient task state machine that drives the CUDA pipeline.
+//
+// Mirrors (behaviour, not code) /root/reference/src/driver_client/dclient.rs and
+// /root/reference/src/ingo_msm/msm_api.rs: same call order tolerance
+// (initialize -> start_process -> set_data -> wait_result -> result), same mode selection
+// ((mem_type, hbm_point_addr) -> DMA / HBM, msm_api.rs:75-95,163-216), same wire sizes
+// (msm_cfg.rs:44-92).  XDMA pwrite/pread become cudaMemcpyAsync into a device arena, register
+// polling becomes CUDA events.  No CPU fallback: without a device every constructor fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/blaze_b200.h"
+#include "msm_internal.h"
+
+using namespace bz;
+
+// ------------------------------------------------------------------------------------ errors
+static thread_local std::string g_last_error;
+
+static int32_t fail(int32_t code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(code, expr)                                                                      \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess) return fail((code), "%s failed: %s", #expr, cudaGetErrorString(_e));   \
+  } while (0)
+
+extern "C" const char* bz_last_error(void) { return g_last_error.c_str(); }
+extern "C" const char* bz_version(void) { return "blaze_b200 0.1.0 sm_100a"; }
+
+// ------------------------------------------------------------------------------------ DriverClient
+// Card address space: [0, ARENA_LIMIT) is HBM (a growable device arena).  The MSM stream ports of
+// the reference (msm_cfg.rs:44-92: 0x0000_0100_0000_0000 / 0x0000_0200_0000_0000) lie above it and
+// are served by bz_msm_set_data, never by dma_write.
+static const uint64_t ARENA_LIMIT = 1ull << 40;
+static const size_t ARENA_GRAIN = 64ull << 20;
+
+struct bz_dclient {
+  int device = 0;
+  int card_type = BZ_CARD_B200;
+  cudaStream_t stream = nullptr;
+  uint8_t* arena = nullptr;
+  size_t arena_cap = 0;
+  uint64_t epoch = 1;   // bumped on every arena write: invalidates cached Montgomery tables
+  std::mutex mu;
+};
+
+static int32_t dc_select(bz_dclient* dc) {
+  if (!dc) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null DriverClient");
+  CUDA_TRY(BZ_ERR_NO_DEVICE, cudaSetDevice(dc->device));
+  return BZ_OK;
+}
+
+static int32_t arena_reserve(bz_dclient* dc, uint64_t end) {
+  if (end > ARENA_LIMIT) return fail(BZ_ERR_WRITE, "address 0x%llx beyond the HBM window", (unsigned long long)end);
+  if (end <= dc->arena_cap) return BZ_OK;
+  size_t cap = (size_t)((end + ARENA_GRAIN - 1) / ARENA_GRAIN * ARENA_GRAIN);
+  uint8_t* p = nullptr;
+  CUDA_TRY(BZ_ERR_WRITE, cudaMalloc(&p, cap));
+  if (dc->arena_cap) CUDA_TRY(BZ_ERR_WRITE, cudaMemcpyAsync(p, dc->arena, dc->arena_cap, cudaMemcpyDeviceToDevice, dc->stream));
+  CUDA_TRY(BZ_ERR_WRITE, cudaMemsetAsync(p + dc->arena_cap, 0, cap - dc->arena_cap, dc->stream));
+  CUDA_TRY(BZ_ERR_WRITE, cudaStreamSynchronize(dc->stream));
+  if (dc->arena) cudaFree(dc->arena);
+  dc->arena = p;
+  dc->arena_cap = cap;
+  return BZ_OK;
+}
+
+extern "C" int32_t bz_dclient_new(const char* id, int32_t card_type, bz_dclient** out) {
+  if (!out) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "out is null");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(BZ_ERR_NO_DEVICE, "no CUDA device (%s); blaze_b200 has no CPU fallback",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  int dev = id && *id ? atoi(id) : 0;
+  if (dev < 0 || dev >= ndev) return fail(BZ_ERR_NO_DEVICE, "device id '%s' out of range (%d devices)", id, ndev);
+  bz_dclient* dc = new bz_dclient();
+  dc->device = dev;
+  dc->card_type = card_type;
+  if (cudaSetDevice(dev) != cudaSuccess || cudaStreamCreateWithFlags(&dc->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete dc;
+    return fail(BZ_ERR_NO_DEVICE, "cannot initialise device %d: %s", dev, cudaGetErrorString(cudaGetLastError()));
+  }
+  *out = dc;
+  return BZ_OK;
+}
+
+extern "C" int32_t bz_dclient_free(bz_dclient* dc) {
+  if (!dc) return BZ_OK;
+  cudaSetDevice(dc->device);
+  if (dc->stream) { cudaStreamSynchronize(dc->stream); cudaStreamDestroy(dc->stream); }
+  if (dc->arena) cudaFree(dc->arena);
+  delete dc;
+  return BZ_OK;
+}
+
+extern "C" int32_t bz_dclient_reset(bz_dclient* dc) {
+  int32_t rc = dc_select(dc);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(dc->mu);
+  CUDA_TRY(BZ_ERR_UNKNOWN, cudaStreamSynchronize(dc->stream));
+  if (dc->arena) CUDA_TRY(BZ_ERR_UNKNOWN, cudaMemsetAsync(dc->arena, 0, dc->arena_cap, dc->stream));
+  dc->epoch++;
+  return BZ_OK;
+}
+
+extern "C" int32_t bz_dclient_dma_write(bz_dclient* dc, uint64_t base, uint64_t offset, const uint8_t* data, size_t len) {
+  int32_t rc = dc_select(dc);
+  if (rc) return rc;
+  if (!data && len) return fail(BZ_ERR_WRITE, "null data");
+  std::lock_guard<std::mutex> lk(dc->mu);
+  uint64_t a = base + offset;
+  if (a < base || a + len < a) return fail(BZ_ERR_WRITE, "address overflow");
+  rc = arena_reserve(dc, a + len);
+  if (rc) return rc;
+  CUDA_TRY(BZ_ERR_WRITE, cudaMemcpyAsync(dc->arena + a, data, len, cudaMemcpyHostToDevice, dc->stream));
+  CUDA_TRY(BZ_ERR_WRITE, cudaStreamSynchronize(dc->stream));   // caller may free `data` on return
+  dc->epoch++;
+  return BZ_OK;
+}
+
+extern "C" int32_t bz_dclient_dma_read(bz_dclient* dc, uint64_t base, uint64_t offset, uint8_t* out, size_t len) {
+  int32_t rc = dc_select(dc);
+  if (rc) return rc;
+  if (!out && len) return fail(BZ_ERR_READ, "null out");
+  std::lock_guard<std::mutex> lk(dc->mu);
+  uint64_t a = base + offset;
+  if (a + len > ARENA_LIMIT) return fail(BZ_ERR_READ, "address 0x%llx beyond the HBM window", (unsigned long long)a);
+  // never-written HBM reads back as zeros
+  size_t have = a < dc->arena_cap ? (size_t)std::min<uint64_t>(len, dc->arena_cap - a) : 0;
+  if (have) {
+    CUDA_TRY(BZ_ERR_READ, cudaMemcpyAsync(out, dc->arena + a, have, cudaMemcpyDeviceToHost, dc->stream));
+    CUDA_TRY(BZ_ERR_READ, cudaStreamSynchronize(dc->stream));
+  }
+  if (have < len) memset(out + have, 0, len - have);
+  return BZ_OK;
+}
+
+extern "C" int32_t bz_dclient_firewalls_status(bz_dclient* dc, uint32_t* blocked_mask) {
+  if (!dc) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null DriverClient");
+  if (blocked_mask) *blocked_mask = 0;
+  return BZ_OK;
+}
+extern "C" int32_t bz_dclient_unblock_firewalls(bz_dclient* dc) { return dc ? BZ_OK : fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null DriverClient"); }
+extern "C" int32_t bz_dclient_initialize_cms(bz_dclient* dc) { return dc ? BZ_OK : fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null DriverClient"); }
+extern "C" int32_t bz_dclient_reset_sensor_data(bz_dclient* dc) { return dc ? BZ_OK : fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null DriverClient"); }
+extern "C" int32_t bz_dclient_setup_before_load_binary(bz_dclient* dc) { return dc ? BZ_OK : fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null DriverClient"); }
+extern "C" int32_t bz_dclient_load_binary(bz_dclient* dc, const uint8_t*, size_t) {
+  // The kernels are part of this library (fatbin, sm_100a); there is no image to load.
+  return dc ? BZ_OK : fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null DriverClient");
+}
+
+extern "C" int32_t bz_dclient_device_info(bz_dclient* dc, char* name, size_t name_len, uint64_t* hbm_total, uint64_t* hbm_free) {
+  int32_t rc = dc_select(dc);
+  if (rc) return rc;
+  cudaDeviceProp prop;
+  CUDA_TRY(BZ_ERR_READ, cudaGetDeviceProperties(&prop, dc->device));
+  if (name && name_len) { strncpy(name, prop.name, name_len - 1); name[name_len - 1] = 0; }
+  size_t f = 0, t = 0;
+  CUDA_TRY(BZ_ERR_READ, cudaMemGetInfo(&f, &t));
+  if (hbm_total) *hbm_total = t;
+  if (hbm_free) *hbm_free = f;
+  return BZ_OK;
+}
+
+extern "C" int32_t bz_host_alloc(size_t bytes, void** out) {
+  if (!out) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "out is null");
+  CUDA_TRY(BZ_ERR_NO_DEVICE, cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+  return BZ_OK;
+}
+extern "C" int32_t bz_host_free(void* p) {
+  if (p) CUDA_TRY(BZ_ERR_UNKNOWN, cudaFreeHost(p));
+  return BZ_OK;
+}
+
+// ------------------------------------------------------------------------------------ MSM planning
+static const CurveOps* ops_for(int curve) {
+  switch (curve) {
+    case BZ_CURVE_BLS377: return curve_ops_bls12_377();
+    case BZ_CURVE_BN254: return curve_ops_bn254();
+    case BZ_CURVE_BLS381: return curve_ops_bls12_381();
+  }
+  return nullptr;
+}
+
+// 288-bit little-endian helper for window planning
+struct Big9 {
+  uint32_t v[9];
+};
+static void big_add_pow2(Big9& a, int bit) {   // a += 2^bit
+  uint64_t carry = 1ull << (bit & 31);
+  for (int k = bit >> 5; k < 9 && carry; k++) {
+    uint64_t t = (uint64_t)a.v[k] + carry;
+    a.v[k] = (uint32_t)t;
+    carry = t >> 32;
+  }
+}
+static uint64_t big_shr(const Big9& a, int bit) {   // (a >> bit) truncated to 64 bits
+  uint64_t r = 0;
+  for (int i = 0; i < 64; i++) {
+    int b = bit + i;
+    if (b >= 288) break;
+    if ((a.v[b >> 5] >> (b & 31)) & 1) r |= 1ull << i;
+  }
+  return r;
+}
+
+// Number of windows for c-bit signed digits so that the TOP (unsigned) digit of the largest legal
+// scalar `smax` stays <= 2^(c-1); fills K = sum_{w<W-1} 2^(c-1+cw).
+static int plan_windows(const uint32_t smax[8], int sbits, int c, DigitConst& dc) {
+  for (int W = std::max(1, (sbits + c - 1) / c);; W++) {
+    Big9 k;
+    memset(&k, 0, sizeof(k));
+    for (int w = 0; w < W - 1; w++) big_add_pow2(k, c - 1 + c * w);
+    Big9 s = k;   // s = smax + K
+    uint64_t carry = 0;
+    for (int i = 0; i < 9; i++) {
+      uint64_t t = (uint64_t)s.v[i] + (i < 8 ? smax[i] : 0) + carry;
+      s.v[i] = (uint32_t)t;
+      carry = t >> 32;
+    }
+    // with W >= ceil(sbits/c) the shifted value has at most c+2 bits, so 64 bits are enough
+    if (big_shr(s, c * (W - 1)) <= (1ull << (c - 1))) {
+      memcpy(dc.K, k.v, sizeof(dc.K));
+      return W;
+    }
+  }
+}
+
+static const int RESULT_SLOTS = 16;     // max tasks in flight per client
+static const int RESULT_SLOT_BYTES = 272;   // 3*48 result bytes + error word, 16-byte aligned
+
+struct MsmTaskResult {
+  std::vector<uint8_t> bytes;   // filled from the pinned slot when the event has completed
+  uint32_t label = 0;
+  cudaEvent_t done = nullptr;
+  uint8_t* host_slot = nullptr;   // pinned (slot of bz_msm::pinned)
+  int* host_err = nullptr;        // pinned
+  bool collected = false;
+  int32_t status = BZ_OK;
+};
+
+struct bz_msm {
+  bz_dclient* dc = nullptr;
+  const CurveOps* ops = nullptr;
+  int curve = 0, mem_type = BZ_MEM_DMA, factor = 1;
+  // "registers" of the reference core
+  uint32_t nof_elements = 0;
+  bool hbm_mode = false;
+  uint64_t hbm_addr = 0, hbm_off = 0;
+  uint32_t next_label = 0, last_label = 0;
+  int forced_c = 0;
+  // task state machine
+  int pending_tasks = 0;     // start_process() calls not yet matched with data
+  bool data_ready = false;   // set_data() arrived, not yet consumed by a task
+  uint64_t data_M = 0;
+  std::deque<MsmTaskResult> results;
+  // device state
+  MsmPlan plan{};
+  bool have_plan = false;
+  MsmWorkspace ws{};
+  std::vector<void*> ws_allocs;
+  void* table = nullptr;
+  uint64_t table_cap = 0, table_n = 0, table_addr = ~0ull, table_epoch = 0;
+  bool table_from_arena = false;
+  uint8_t* dma_points = nullptr;
+  size_t dma_points_cap = 0;
+  uint32_t* scalars_dev = nullptr;
+  size_t scalars_cap = 0;
+  const uint32_t* scalars_src = nullptr;   // where the pending task reads its scalars from
+  uint8_t* pinned = nullptr;   // RESULT_SLOTS result slots
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // start, sorted, acc begin, acc end, done
+  float last_ms[4] = {0, 0, 0, 0};
+  bool timed = false;
+  std::mutex mu;
+};
+
+static void ws_free(bz_msm* m) {
+  for (void* p : m->ws_allocs) cudaFree(p);
+  m->ws_allocs.clear();
+  memset(&m->ws, 0, sizeof(m->ws));
+  m->have_plan = false;
+}
+
+template <class T>
+static cudaError_t ws_alloc(bz_msm* m, T** p, size_t bytes) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, bytes ? bytes : 16);
+  if (e == cudaSuccess) { m->ws_allocs.push_back(q); *p = (T*)q; }
+  return e;
+}
+
+static int ilog2_floor(uint64_t v) { int l = 0; while (v >>= 1) l++; return l; }
+
+static int32_t make_plan(bz_msm* m, uint64_t M, int words_per_scalar) {
+  if (m->have_plan && m->plan.M == M && m->plan.words_per_scalar == words_per_scalar &&
+      (m->forced_c == 0 || m->forced_c == m->plan.c))
+    return BZ_OK;
+  ws_free(m);
+  MsmPlan p{};
+  p.M = M;
+  p.words_per_scalar = words_per_scalar;
+  uint32_t smax[8];
+  int sbits;
+  if (words_per_scalar == 8) {
+    // largest canonical scalar is r - 1
+    memcpy(smax, m->ops->fr_mod, 32);
+    smax[0] -= 1;   // r is odd
+    sbits = m->ops->scalar_bits;
+    memcpy(p.dc.mod, m->ops->fr_mod, 32);
+    p.dc.check_mod = 1;
+  } else {
+    memset(smax, 0, sizeof(smax));
+    smax[0] = 0xffffffffu;
+    sbits = 32;
+    p.dc.check_mod = 0;
+  }
+  // window size: minimise (#mixed adds in accumulation) + (cost of the running-sum reduction)
+  int best_c = 0;
+  double best = 1e300;
+  int env_c = 0;
+  if (const char* e = getenv("BZ_MSM_C")) env_c = atoi(e);
+  int force = m->forced_c ? m->forced_c : env_c;
+  for (int c = 4; c <= 23; c++) {
+    if (force && c != force) continue;
+    DigitConst dcx{};
+    int W = plan_windows(smax, sbits, c, dcx);
+    if ((uint64_t)W * M >= (1ull << 32)) continue;
+    double cost = (double)W * ((double)M + 3.0 * (double)(1ull << (c - 1)));
+    if (cost < best) { best = cost; best_c = c; }
+  }
+  if (!best_c) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "no feasible window size for %llu elements", (unsigned long long)M);
+  p.c = best_c;
+  p.W = plan_windows(smax, sbits, p.c, p.dc);
+  p.nb = (1u << (p.c - 1)) + 1;
+  p.fbits = std::min(10, p.c / 2);
+  p.ncoarse = (int)(((p.nb - 1) >> p.fbits) + 1);
+  p.tile = 65536;
+  p.ntiles = (uint32_t)((M + p.tile - 1) / p.tile);
+  uint64_t total = (uint64_t)p.W * M;
+  // segment length: enough threads to fill the machine several times over, at most 256 entries each
+  uint32_t L = 256;
+  while (L > 16 && total / L < 148ull * 256 * 8) L >>= 1;
+  if (const char* e = getenv("BZ_MSM_SEG")) L = (uint32_t)std::max(1, atoi(e));
+  p.seg_len = L;
+  p.nseg = (total + L - 1) / L;
+  uint32_t nbk = p.nb - 1;
+  p.chunk = std::min<uint32_t>(nbk, 128);
+  if (const char* e = getenv("BZ_MSM_CHUNK")) {
+    uint32_t ch = (uint32_t)atoi(e);
+    if (ch && (ch & (ch - 1)) == 0 && ch <= nbk) p.chunk = ch;
+  }
+  p.nchunks = nbk / p.chunk;
+
+  size_t xb = m->ops->xyzz_bytes;
+  cudaError_t e = cudaSuccess;
+  auto A = [&](auto** ptr, size_t bytes) { if (e == cudaSuccess) e = ws_alloc(m, ptr, bytes); };
+  A(&m->ws.dig, total * 4);
+  A(&m->ws.hmat, (size_t)p.W * p.ntiles * p.ncoarse * 4);
+  A(&m->ws.tot, (size_t)p.W * p.ncoarse * 4);
+  A(&m->ws.base1, (size_t)p.W * (p.ncoarse + 1) * 4);
+  A(&m->ws.l1, total * 8);
+  A(&m->ws.sorted, total * 4);
+  A(&m->ws.goff, ((size_t)p.W * p.nb + 1) * 4);
+  A((uint8_t**)&m->ws.buckets, (size_t)p.W * p.nb * xb);
+  A(&m->ws.part_id, (size_t)p.nseg * 2 * 4);
+  A((uint8_t**)&m->ws.part_pt, (size_t)p.nseg * 2 * xb);
+  A((uint8_t**)&m->ws.red_a, (size_t)p.W * p.nchunks * xb);
+  A((uint8_t**)&m->ws.red_b, (size_t)p.W * std::max<uint32_t>(1, p.nchunks / 2) * xb);
+  A(&m->ws.err, 16);
+  A(&m->ws.result, 256);
+  if (e != cudaSuccess) {
+    ws_free(m);
+    return fail(BZ_ERR_WRITE, "workspace allocation failed for M=%llu c=%d: %s", (unsigned long long)M, p.c, cudaGetErrorString(e));
+  }
+  (void)ilog2_floor;
+  m->plan = p;
+  m->have_plan = true;
+  return BZ_OK;
+}
+
+// ------------------------------------------------------------------------------------ MSM client
+extern "C" int32_t bz_msm_new(bz_dclient* dc, int32_t curve, int32_t mem_type, int32_t is_precompute, bz_msm** out) {
+  if (!out) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "out is null");
+  *out = nullptr;
+  int32_t rc = dc_select(dc);
+  if (rc) return rc;
+  const CurveOps* ops = ops_for(curve);
+  if (!ops) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "unknown curve %d", curve);
+  if (mem_type != BZ_MEM_HBM && mem_type != BZ_MEM_DMA) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "unknown memory type %d", mem_type);
+  bz_msm* m = new bz_msm();
+  m->dc = dc;
+  m->ops = ops;
+  m->curve = curve;
+  m->mem_type = mem_type;
+  m->factor = is_precompute ? 8 : 1;   // PRECOMPUTE_FACTOR / PRECOMPUTE_FACTOR_BASE, msm_api.rs:39-40
+  for (auto& e : m->ev) cudaEventCreate(&e);
+  if (cudaHostAlloc((void**)&m->pinned, (size_t)RESULT_SLOTS * RESULT_SLOT_BYTES, cudaHostAllocDefault) != cudaSuccess) {
+    delete m;
+    return fail(BZ_ERR_NO_DEVICE, "pinned allocation failed");
+  }
+  *out = m;
+  return BZ_OK;
+}
+
+static void result_release(MsmTaskResult& r) {
+  if (r.done) cudaEventDestroy(r.done);
+  r.done = nullptr; r.host_slot = nullptr; r.host_err = nullptr;
+}
+
+extern "C" int32_t bz_msm_free(bz_msm* m) {
+  if (!m) return BZ_OK;
+  cudaSetDevice(m->dc->device);
+  cudaStreamSynchronize(m->dc->stream);
+  for (auto& r : m->results) result_release(r);
+  ws_free(m);
+  if (m->table) cudaFree(m->table);
+  if (m->dma_points) cudaFree(m->dma_points);
+  if (m->scalars_dev) cudaFree(m->scalars_dev);
+  if (m->pinned) cudaFreeHost(m->pinned);
+  for (auto& e : m->ev) if (e) cudaEventDestroy(e);
+  delete m;
+  return BZ_OK;
+}
+
+extern "C" int32_t bz_msm_sizes(bz_msm* m, uint32_t* scalar_size, uint32_t* point_size, uint32_t* result_point_size, uint32_t* precompute_factor) {
+  if (!m) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null MSMClient");
+  if (scalar_size) *scalar_size = 32;
+  if (point_size) *point_size = 2 * m->ops->fq_bytes;
+  if (result_point_size) *result_point_size = 3 * m->ops->fq_bytes;
+  if (precompute_factor) *precompute_factor = m->factor;
+  return BZ_OK;
+}
+
+extern "C" int32_t bz_msm_loaded_binary_parameters(bz_msm* m, uint32_t out[2]) {
+  if (!m || !out) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null argument");
+  // [0] image id, [1] image parameters.  The reference decodes [1] as
+  // reverse_bits().to_be_bytes() unpacked msb0 (msm_api.rs:333-354): after the reversal, LSB-first:
+  // bits 0..3 placeholder, 4..7 #segments, 8..15 bucket addr width, 16..19 #ec adders,
+  // 20..27 curve, 28..31 is_stub.  We synthesise: segments = 1, addr width = current c-1 (or 0),
+  // ec adders = 0xF (saturated: 148 SMs do not fit 4 bits), curve code, is_stub = 0.
+  uint32_t c = m->have_plan ? (uint32_t)(m->plan.c - 1) : 0;
+  uint32_t word = (1u << 4) | ((c & 0xff) << 8) | (0xFu << 16) | (((uint32_t)m->curve & 0xff) << 20);
+  out[0] = 0xB2000000u | (uint32_t)m->curve;
+  out[1] = word;
+  return BZ_OK;
+}
+
+extern "C" int32_t bz_msm_initialize(bz_msm* m, uint32_t nof_elements, int32_t has_hbm_addr, uint64_t hbm_addr, uint64_t hbm_offset) {
+  if (!m) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null MSMClient");
+  std::lock_guard<std::mutex> lk(m->mu);
+  if (m->mem_type == BZ_MEM_DMA && !has_hbm_addr) {
+    m->hbm_mode = false;                      // BASES_SOURCE = 0, msm_api.rs:75-81
+  } else {
+    if (!has_hbm_addr)                        // the reference unwrap()-panics here (msm_api.rs:84)
+      return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "HBM point memory needs hbm_point_addr");
+    m->hbm_mode = true;                       // BASES_SOURCE = 1 + start address, msm_api.rs:82-95
+    m->hbm_addr = hbm_addr;
+    m->hbm_off = hbm_offset;
+  }
+  if (nof_elements == 0) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "nof_elements must be > 0");
+  m->nof_elements = nof_elements;             // NUMBER_OF_MSM_ELEMENTS, msm_api.rs:103-108
+  return BZ_OK;
+}
+
+// enqueue the whole pipeline for one task on the client's stream
+static int32_t launch_task(bz_msm* m) {
+  bz_dclient* dc = m->dc;
+  const uint64_t M = m->data_M;
+  const int wps = m->factor == 8 ? 1 : 8;
+  int32_t rc = make_plan(m, M, wps);
+  if (rc) return rc;
+  cudaStream_t st = dc->stream;
+  MsmTaskResult r;
+  r.label = m->next_label++;
+  m->last_label = r.label;
+  CUDA_TRY(BZ_ERR_UNKNOWN, cudaEventCreateWithFlags(&r.done, cudaEventBlockingSync | cudaEventDisableTiming));
+  if ((int)m->results.size() >= RESULT_SLOTS) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "more than %d results pending; pop them with result()", RESULT_SLOTS);
+  r.host_slot = m->pinned + (size_t)(r.label % RESULT_SLOTS) * RESULT_SLOT_BYTES;
+  r.host_err = reinterpret_cast<int*>(r.host_slot + 256);
+  CUDA_TRY(BZ_ERR_UNKNOWN, cudaMemsetAsync(m->ws.err, 0, 4, st));
+  m->ws.ev_acc0 = m->ev[2];
+  m->ws.ev_acc1 = m->ev[3];
+  cudaEventRecord(m->ev[0], st);
+  launch_msm_sort(m->plan, m->ws, m->scalars_src, st);
+  cudaEventRecord(m->ev[1], st);
+  m->ops->bucket_phase(m->plan, m->ws, m->table, st);
+  cudaEventRecord(m->ev[4], st);
+  m->timed = true;
+  CUDA_TRY(BZ_ERR_UNKNOWN, cudaGetLastError());
+  CUDA_TRY(BZ_ERR_READ, cudaMemcpyAsync(r.host_slot, m->ws.result, 3 * m->ops->fq_bytes, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(BZ_ERR_READ, cudaMemcpyAsync(r.host_err, m->ws.err, 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(BZ_ERR_UNKNOWN, cudaEventRecord(r.done, st));
+  m->results.push_back(r);
+  m->pending_tasks--;
+  m->data_ready = false;
+  return BZ_OK;
+}
+
+extern "C" int32_t bz_msm_start_process(bz_msm* m) {
+  if (!m) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null MSMClient");
+  int32_t rc = dc_select(m->dc);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(m->mu);
+  m->pending_tasks++;                          // PUSH_MSM_TASK_TO_QUEUE, msm_api.rs:113-120
+  if (m->data_ready) return launch_task(m);
+  return BZ_OK;
+}
+
+// make the Montgomery table for `n_points` wire points starting at raw (device pointer)
+static int32_t build_table(bz_msm* m, const uint8_t* raw_dev, uint64_t n_points) {
+  if (m->table_cap < n_points) {
+    if (m->table) cudaFree(m->table);
+    m->table = nullptr;
+    m->table_cap = 0;
+    CUDA_TRY(BZ_ERR_WRITE, cudaMalloc(&m->table, n_points * m->ops->affine_bytes));
+    m->table_cap = n_points;
+  }
+  m->ops->points_to_mont(raw_dev, m->table, n_points, m->dc->stream);
+  CUDA_TRY(BZ_ERR_UNKNOWN, cudaGetLastError());
+  m->table_n = n_points;
+  return BZ_OK;
+}
+
+static int32_t ensure_arena_table(bz_msm* m, uint64_t addr, uint64_t n_points) {
+  bz_dclient* dc = m->dc;
+  if (m->table_from_arena && m->table_addr == addr && m->table_n == n_points && m->table_epoch == dc->epoch) return BZ_OK;
+  uint64_t bytes = n_points * 2ull * m->ops->fq_bytes;
+  if (addr & 15) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "hbm point address must be 16-byte aligned");
+  {
+    std::lock_guard<std::mutex> lk(dc->mu);
+    int32_t rc = arena_reserve(dc, addr + bytes);   // unwritten HBM reads as zeros = identity padding
+    if (rc) return rc;
+  }
+  int32_t rc = build_table(m, dc->arena + addr, n_points);
+  if (rc) return rc;
+  m->table_from_arena = true;
+  m->table_addr = addr;
+  m->table_epoch = dc->epoch;
+  return BZ_OK;
+}
+
+static int32_t stage_scalars(bz_msm* m, const uint8_t* scalars, size_t len) {
+  if (m->scalars_cap < len) {
+    if (m->scalars_dev) cudaFree(m->scalars_dev);
+    m->scalars_dev = nullptr;
+    m->scalars_cap = 0;
+    CUDA_TRY(BZ_ERR_WRITE, cudaMalloc((void**)&m->scalars_dev, len));
+    m->scalars_cap = len;
+  }
+  CUDA_TRY(BZ_ERR_WRITE, cudaMemcpyAsync(m->scalars_dev, scalars, len, cudaMemcpyHostToDevice, m->dc->stream));
+  m->scalars_src = m->scalars_dev;
+  return BZ_OK;
+}
+
+static int32_t set_data_common(bz_msm* m, const uint8_t* points, size_t points_len, const uint8_t* scalars_host,
+                               uint64_t scalars_dev_ptr, size_t scalars_len, uint32_t nof_elements,
+                               int32_t has_hbm_addr, uint64_t hbm_addr, uint64_t hbm_offset) {
+  int32_t rc = dc_select(m->dc);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(m->mu);
+  const uint64_t n = nof_elements;
+  const uint64_t ps = 2ull * m->ops->fq_bytes * m->factor;   // bytes per element record
+  if (n == 0) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "nof_elements must be > 0");
+  // The reference trusts lengths (last chunk is "whatever is left", msm_api.rs:166-170); we validate.
+  if (scalars_len != n * 32) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "scalars length %zu != %llu*32", scalars_len, (unsigned long long)n);
+  if (points && points_len != n * ps) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "points length %zu != %llu*%llu", points_len, (unsigned long long)n, (unsigned long long)ps);
+  if (!points && !has_hbm_addr) return BZ_OK;   // (None, None): the reference silently does nothing (msm_api.rs:163-216)
+  const uint64_t npts = n * m->factor;
+  if (npts >= (1ull << 31)) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "too many points");
+  // a new input replaces a previous un-consumed one only after the stream has drained it
+  if (points && !has_hbm_addr) {
+    // DMA mode: points streamed with the call (msm_api.rs:175-202)
+    if (m->dma_points_cap < points_len) {
+      if (m->dma_points) cudaFree(m->dma_points);
+      m->dma_points = nullptr;
+      m->dma_points_cap = 0;
+      CUDA_TRY(BZ_ERR_WRITE, cudaMalloc((void**)&m->dma_points, points_len));
+      m->dma_points_cap = points_len;
+    }
+    CUDA_TRY(BZ_ERR_WRITE, cudaMemcpyAsync(m->dma_points, points, points_len, cudaMemcpyHostToDevice, m->dc->stream));
+    rc = build_table(m, m->dma_points, npts);
+    if (rc) return rc;
+    m->table_from_arena = false;
+  } else {
+    uint64_t a = hbm_addr + hbm_offset;
+    if (points) {
+      // preload to HBM, then scalars (msm_api.rs:203-216)
+      rc = bz_dclient_dma_write(m->dc, hbm_addr, hbm_offset, points, points_len);
+      if (rc) return rc;
+      m->hbm_mode = true; m->hbm_addr = hbm_addr; m->hbm_off = hbm_offset;
+    }
+    rc = ensure_arena_table(m, a, npts);
+    if (rc) return rc;
+  }
+  if (scalars_host) {
+    rc = stage_scalars(m, scalars_host, scalars_len);
+    if (rc) return rc;
+    // the caller may drop its buffers when we return (move-in semantics)
+    CUDA_TRY(BZ_ERR_WRITE, cudaStreamSynchronize(m->dc->stream));
+  } else {
+    m->scalars_src = reinterpret_cast<const uint32_t*>(scalars_dev_ptr);
+  }
+  m->data_M = npts;
+  m->data_ready = true;
+  if (m->pending_tasks > 0) return launch_task(m);
+  return BZ_OK;
+}
+
+extern "C" int32_t bz_msm_set_data(bz_msm* m, const uint8_t* points, size_t points_len, const uint8_t* scalars, size_t scalars_len,
+                                   uint32_t nof_elements, int32_t has_hbm_addr, uint64_t hbm_addr, uint64_t hbm_offset) {
+  if (!m) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null MSMClient");
+  if (!scalars) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null scalars");
+  return set_data_common(m, points, points_len, scalars, 0, scalars_len, nof_elements, has_hbm_addr, hbm_addr, hbm_offset);
+}
+
+extern "C" int32_t bz_msm_set_scalars_device(bz_msm* m, uint64_t scalars_dev_ptr, uint32_t nof_elements, int32_t has_hbm_addr,
+                                             uint64_t hbm_addr, uint64_t hbm_offset) {
+  if (!m) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null MSMClient");
+  if (!scalars_dev_ptr || (scalars_dev_ptr & 15)) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "device scalar pointer must be 16-byte aligned");
+  if (!has_hbm_addr) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "device scalars need HBM-resident points");
+  return set_data_common(m, nullptr, 0, nullptr, scalars_dev_ptr, (size_t)nof_elements * 32, nof_elements, has_hbm_addr, hbm_addr, hbm_offset);
+}
+
+static int32_t collect(bz_msm* m, MsmTaskResult& r) {
+  if (r.collected) return r.status;
+  CUDA_TRY(BZ_ERR_READ, cudaEventSynchronize(r.done));
+  r.bytes.assign(r.host_slot, r.host_slot + 3 * m->ops->fq_bytes);
+  int err = *r.host_err;
+  r.status = err == BZ_ERR_NONE ? BZ_OK : BZ_ERR_INVALID_PRIMITIVE_PARAM;
+  r.collected = true;
+  if (m->timed) {
+    float a = 0, b = 0, k = 0;
+    cudaEventElapsedTime(&a, m->ev[0], m->ev[4]);
+    cudaEventElapsedTime(&b, m->ev[0], m->ev[1]);
+    cudaEventElapsedTime(&k, m->ev[2], m->ev[3]);
+    m->last_ms[0] = a;
+    m->last_ms[1] = b;
+    m->last_ms[2] = k;           // k_accumulate alone
+    m->last_ms[3] = a - b - k;   // memset + merge + reduce + finish
+  }
+  if (r.status) return fail(r.status, "device flagged a non-canonical scalar (>= r)");
+  return BZ_OK;
+}
+
+extern "C" int32_t bz_msm_wait_result(bz_msm* m) {
+  if (!m) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null MSMClient");
+  int32_t rc = dc_select(m->dc);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(m->mu);
+  if (m->results.empty()) return fail(BZ_ERR_NO_RESULT, "no task in flight (the reference would spin forever on RESULT_VALID)");
+  return collect(m, m->results.front());
+}
+
+extern "C" int32_t bz_msm_result(bz_msm* m, uint8_t* out, size_t out_len, uint32_t* result_label) {
+  if (!m || !out) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null argument");
+  int32_t rc = dc_select(m->dc);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(m->mu);
+  if (m->results.empty()) return fail(BZ_ERR_NO_RESULT, "result queue is empty");
+  size_t need = 3 * (size_t)m->ops->fq_bytes;
+  if (out_len < need) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "result buffer too small (%zu < %zu)", out_len, need);
+  MsmTaskResult& r = m->results.front();
+  rc = collect(m, r);
+  if (rc == BZ_OK) {
+    memcpy(out, r.bytes.data(), need);
+    if (result_label) *result_label = r.label;
+  }
+  result_release(r);
+  m->results.pop_front();                      // POP_RESULT, msm_api.rs:265-269
+  return rc;
+}
+
+extern "C" int32_t bz_msm_task_label(bz_msm* m, uint32_t* label) {
+  if (!m || !label) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null argument");
+  *label = m->last_label;
+  return BZ_OK;
+}
+extern "C" int32_t bz_msm_nof_elements(bz_msm* m, uint32_t* n) {
+  if (!m || !n) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null argument");
+  *n = m->nof_elements;
+  return BZ_OK;
+}
+extern "C" int32_t bz_msm_is_msm_engine_ready(bz_msm* m, uint32_t* ready) {
+  if (!m || !ready) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null argument");
+  *ready = 1;
+  return BZ_OK;
+}
+
+extern "C" int32_t bz_msm_load_data_to_hbm(bz_msm* m, const uint8_t* points, size_t len, uint64_t addr, uint64_t offset) {
+  if (!m) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null MSMClient");
+  {
+    std::lock_guard<std::mutex> lk(m->mu);
+    m->hbm_mode = true;                        // BASES_SOURCE = 1 + start address, msm_api.rs:299-311
+    m->hbm_addr = addr;
+  }
+  return bz_dclient_dma_write(m->dc, addr, offset, points, len);
+}
+extern "C" int32_t bz_msm_get_data_from_hbm(bz_msm* m, uint8_t* out, size_t len, uint64_t addr, uint64_t offset) {
+  if (!m) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null MSMClient");
+  return bz_dclient_dma_read(m->dc, addr, offset, out, len);
+}
+
+extern "C" int32_t bz_msm_phase_times(bz_msm* m, float ms[4]) {
+  if (!m || !ms) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null argument");
+  memcpy(ms, m->last_ms, sizeof(m->last_ms));
+  return BZ_OK;
+}
+extern "C" int32_t bz_msm_set_window_bits(bz_msm* m, int32_t c) {
+  if (!m) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null MSMClient");
+  if (c != 0 && (c < 4 || c > 23)) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "window bits must be 0 or in [4, 23]");
+  std::lock_guard<std::mutex> lk(m->mu);
+  m->forced_c = c;
+  return BZ_OK;
+}
+extern "C" int32_t bz_msm_plan_info(bz_msm* m, uint32_t out[4]) {
+  if (!m || !out) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null argument");
+  out[0] = m->have_plan ? m->plan.c : 0;
+  out[1] = m->have_plan ? m->plan.W : 0;
+  out[2] = m->have_plan ? m->plan.nb : 0;
+  out[3] = m->have_plan ? m->plan.seg_len : 0;
+  return BZ_OK;
+}
+
+extern "C" int32_t bz_msm_combine_results(bz_msm* m, const uint8_t* records, int32_t n, uint8_t* out, size_t out_len) {
+  if (!m || !records || !out || n <= 0) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "bad argument");
+  int32_t rc = dc_select(m->dc);
+  if (rc) return rc;
+  size_t rs = 3 * (size_t)m->ops->fq_bytes;
+  if (out_len < rs) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "result buffer too small");
+  uint8_t* d = nullptr;
+  CUDA_TRY(BZ_ERR_WRITE, cudaMalloc((void**)&d, rs * (n + 1)));
+  cudaStream_t st = m->dc->stream;
+  cudaMemcpyAsync(d, records, rs * n, cudaMemcpyHostToDevice, st);
+  m->ops->combine_results(d, n, d + rs * n, st);
+  cudaMemcpyAsync(out, d + rs * n, rs, cudaMemcpyDeviceToHost, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(BZ_ERR_UNKNOWN, "combine failed: %s", cudaGetErrorString(e));
+  return BZ_OK;
+}
+
+extern "C" int32_t bz_msm_generate_chain_points(bz_msm* m, const uint8_t* p0q, size_t p0q_len, uint64_t first, uint64_t n,
+                                                uint64_t addr, uint64_t offset) {
+  if (!m || !p0q) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null argument");
+  int32_t rc = dc_select(m->dc);
+  if (rc) return rc;
+  size_t ps = 2 * (size_t)m->ops->fq_bytes;
+  if (p0q_len != 2 * ps) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "p0q must be two wire points");
+  if (m->factor != 1) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "chain generator writes factor-1 bases");
+  bz_dclient* dc = m->dc;
+  uint64_t a = addr + offset;
+  if (a & 15) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "address must be 16-byte aligned");
+  std::lock_guard<std::mutex> lk(dc->mu);
+  rc = arena_reserve(dc, a + n * ps);
+  if (rc) return rc;
+  uint8_t* d = nullptr;
+  CUDA_TRY(BZ_ERR_WRITE, cudaMalloc((void**)&d, 2 * ps));
+  cudaMemcpyAsync(d, p0q, 2 * ps, cudaMemcpyHostToDevice, dc->stream);
+  m->ops->gen_chain_points(d, first, n, dc->arena + a, dc->stream);
+  cudaError_t e = cudaStreamSynchronize(dc->stream);
+  cudaFree(d);
+  dc->epoch++;
+  if (e != cudaSuccess) return fail(BZ_ERR_UNKNOWN, "generator failed: %s", cudaGetErrorString(e));
+  return BZ_OK;
+}
+
+extern "C" int32_t bz_msm_field_selftest(bz_msm* m, const uint8_t* a, const uint8_t* b, uint8_t* out, int32_t n, int32_t op) {
+  if (!m || !a || !b || !out || n <= 0) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "bad argument");
+  int32_t rc = dc_select(m->dc);
+  if (rc) return rc;
+  size_t bytes = (size_t)n * m->ops->fq_bytes;
+  uint8_t* d = nullptr;
+  CUDA_TRY(BZ_ERR_WRITE, cudaMalloc((void**)&d, 3 * bytes));
+  cudaStream_t st = m->dc->stream;
+  cudaMemcpyAsync(d, a, bytes, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(d + bytes, b, bytes, cudaMemcpyHostToDevice, st);
+  m->ops->field_selftest(d, d + bytes, d + 2 * bytes, n, op, st);
+  cudaMemcpyAsync(out, d + 2 * bytes, bytes, cudaMemcpyDeviceToHost, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(BZ_ERR_UNKNOWN, "selftest failed: %s", cudaGetErrorString(e));
+  return BZ_OK;
+}

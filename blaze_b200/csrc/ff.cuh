@@ -4,15 +4,16 @@
 // fields, 8 limbs for the 254/255-bit fields).  All values are kept fully reduced in
 // [0, p); "Montgomery form" means a*R mod p with R = 2^(32 N).
 //
-// mul() is a word-serial Montgomery product arranged as two interleaved accumulators
-// ("even"/"odd" columns) so that every 32x32->64 partial product and its carry lands in one
-// IMAD.WIDE.U32(.X): per multiplier limb b[i] the schedule is
-//     odd  = (odd >> 64) + a[1,3,5..]*b[i]      (carry-in from the even[0]+odd[1] fold)
-//     even =  even       + a[0,2,4..]*b[i]
-//     m    = even[0] * (-p^-1 mod 2^32)
-//     odd +=  p[1,3,5..]*m ;  even += p[0,2,4..]*m        => even[0] == 0
+// mul() is a word-serial Montgomery product arranged as two interleaved sets of 64-bit
+// accumulator columns ("even" = limb pairs (2k,2k+1), "odd" = pairs (2k+1,2k+2)) so that every
+// 32x32->64 partial product plus its 64-bit accumulate-with-carry is ONE IMAD.WIDE.U32(.X)
+// (ptxas fuses mul.wide.u32 + add(c).cc.u64).  Per multiplier limb b[i]:
+//     odd  = (odd >> 64) + a[1,3,5..]*b[i]
+//     even =  even + hi32(old odd[0]) + a[0,2,4..]*b[i]
+//     m    = lo32(even[0]) * (-p^-1 mod 2^32)
+//     odd +=  p[1,3,5..]*m ;  even += p[0,2,4..]*m        => lo32(even[0]) == 0
 // and the roles of the two arrays swap for the next limb (that swap IS the divide by 2^32).
-// N*(2N+1) multiply instructions per product (300 for N=12, 136 for N=8).
+// About N*(2N+3) multiplier-pipe instructions per product.
 //
 // What the reference does here: nothing -- the arithmetic of /root/reference lives in an FPGA
 // bitstream; the semantics (arkworks Fp Montgomery arithmetic) are restated by oracle/.
@@ -93,68 +94,65 @@ struct ff {
   }
   BZ_HDI static E neg(const E& a) { return sub(zero(), a); }
 
-  // ---- Montgomery product building blocks (see header) ----
-  // acc[0..N) = sum_{j even} a[j]*bi * 2^(32 j)            (fresh, no carries needed)
-  BZ_HDI static void mul_n(uint32_t* acc, const uint32_t* a, uint32_t bi) {
-#pragma unroll
-    for (int j = 0; j < N; j += 2) {
-      acc[j] = cc::mul_lo(a[j], bi);
-      acc[j + 1] = cc::mul_hi(a[j], bi);
-    }
-  }
-  // acc[0..N) += sum_{j even} a[j]*bi * 2^(32 j); carry-out left in CC
-  BZ_HDI static void cmad_n(uint32_t* acc, const uint32_t* a, uint32_t bi) {
-    acc[0] = cc::mad_lo_cc(a[0], bi, acc[0]);
-    acc[1] = cc::madc_hi_cc(a[0], bi, acc[1]);
-#pragma unroll
-    for (int j = 2; j < N; j += 2) {
-      acc[j] = cc::madc_lo_cc(a[j], bi, acc[j]);
-      acc[j + 1] = cc::madc_hi_cc(a[j], bi, acc[j + 1]);
-    }
-  }
-  // odd = (odd >> 64) + sum_{j even} a[j]*bi * 2^(32 j), carry-in from CC, no carry-out
-  BZ_HDI static void madc_n_rshift(uint32_t* odd, const uint32_t* a, uint32_t bi) {
-#pragma unroll
-    for (int j = 0; j < N - 2; j += 2) {
-      odd[j] = cc::madc_lo_cc(a[j], bi, odd[j + 2]);
-      odd[j + 1] = cc::madc_hi_cc(a[j], bi, odd[j + 3]);
-    }
-    odd[N - 2] = cc::madc_lo_cc(a[N - 2], bi, 0u);
-    odd[N - 1] = cc::madc_hi(a[N - 2], bi, 0u);
-  }
-  // one multiplier limb: T = (T + a*bi + m*p) / 2^32 in the even/odd representation
+  // ---- Montgomery product (see header) ----
+  // One multiplier limb.  E ("even") holds 64-bit columns (2k, 2k+1), O ("odd") columns
+  // (2k+1, 2k+2):  T = E + 2^32 * O.  On entry of a non-first step O is the previous step's E,
+  // whose low 32 bits are zero after the reduction, so  T_prev / 2^32 = E + hi32(O[0]) + 2^32 * (O >> 64).
   template <bool FIRST>
-  BZ_HDI static void mad_n_redc(uint32_t* even, uint32_t* odd, const uint32_t* a, uint32_t bi) {
+  BZ_HDI static void step(uint64_t* Ev, uint64_t* Ov, const uint32_t* a, uint32_t bi) {
+    constexpr int NW = N / 2;
     if (FIRST) {
-      mul_n(odd, a + 1, bi);
-      mul_n(even, a, bi);
+#pragma unroll
+      for (int k = 0; k < NW; k++) {
+        Ov[k] = cc::mul_wide(a[2 * k + 1], bi);
+        Ev[k] = cc::mul_wide(a[2 * k], bi);
+      }
     } else {
-      even[0] = cc::add_cc(even[0], odd[1]);
-      madc_n_rshift(odd, a + 1, bi);
-      cmad_n(even, a, bi);
-      odd[N - 1] = cc::addc(odd[N - 1], 0u);
+      uint64_t h = Ov[0] >> 32;
+      // O' = (O >> 64) + a[odd] * bi
+      Ov[0] = cc::add_cc64(Ov[1], cc::mul_wide(a[1], bi));
+#pragma unroll
+      for (int k = 1; k < NW - 1; k++) Ov[k] = cc::addc_cc64(Ov[k + 1], cc::mul_wide(a[2 * k + 1], bi));
+      Ov[NW - 1] = cc::addc64(0ull, cc::mul_wide(a[N - 1], bi));
+      // E' = E + h + a[even] * bi
+      Ev[0] = cc::add_cc64(Ev[0], cc::mad_wide(a[0], bi, h));
+#pragma unroll
+      for (int k = 1; k < NW; k++) Ev[k] = cc::addc_cc64(Ev[k], cc::mul_wide(a[2 * k], bi));
+      uint64_t c = cc::addc64(0ull, 0ull);
+      Ov[NW - 1] += c << 32;
     }
-    uint32_t mi = even[0] * F::INV;
-    cmad_n(odd, F::mod() + 1, mi);
-    cmad_n(even, F::mod(), mi);
-    odd[N - 1] = cc::addc(odd[N - 1], 0u);
+    uint32_t m = (uint32_t)Ev[0] * F::INV;
+    Ov[0] = cc::add_cc64(Ov[0], cc::mul_wide(F::mod()[1], m));
+#pragma unroll
+    for (int k = 1; k < NW - 1; k++) Ov[k] = cc::addc_cc64(Ov[k], cc::mul_wide(F::mod()[2 * k + 1], m));
+    Ov[NW - 1] = cc::addc64(Ov[NW - 1], cc::mul_wide(F::mod()[N - 1], m));
+    Ev[0] = cc::add_cc64(Ev[0], cc::mul_wide(F::mod()[0], m));
+#pragma unroll
+    for (int k = 1; k < NW; k++) Ev[k] = cc::addc_cc64(Ev[k], cc::mul_wide(F::mod()[2 * k], m));
+    uint64_t c2 = cc::addc64(0ull, 0ull);
+    Ov[NW - 1] += c2 << 32;
   }
 
   // r = a*b/R mod p
   BZ_HDI static E mul(const E& a, const E& b) {
-    uint32_t even[N], odd[N];
+    constexpr int NW = N / 2;
+    uint64_t Ev[NW], Ov[NW];
 #pragma unroll
     for (int i = 0; i < N; i += 2) {
-      if (i == 0) mad_n_redc<true>(even, odd, a.v, b.v[0]);
-      else        mad_n_redc<false>(even, odd, a.v, b.v[i]);
-      mad_n_redc<false>(odd, even, a.v, b.v[i + 1]);
+      if (i == 0) step<true>(Ev, Ov, a.v, b.v[0]);
+      else        step<false>(Ev, Ov, a.v, b.v[i]);
+      step<false>(Ov, Ev, a.v, b.v[i + 1]);
     }
-    // T = even + (odd >> 32)
+    // last step had Ov in the "even" role: T = Ev + (Ov >> 32)
     E r;
-    r.v[0] = cc::add_cc(even[0], odd[1]);
+    r.v[0] = cc::add_cc((uint32_t)Ev[0], (uint32_t)(Ov[0] >> 32));
 #pragma unroll
-    for (int i = 1; i < N - 1; i++) r.v[i] = cc::addc_cc(even[i], odd[i + 1]);
-    r.v[N - 1] = cc::addc(even[N - 1], 0u);
+    for (int j = 1; j < N - 1; j++) {
+      uint32_t e = (j & 1) ? (uint32_t)(Ev[j / 2] >> 32) : (uint32_t)Ev[j / 2];
+      uint32_t o = ((j + 1) & 1) ? (uint32_t)(Ov[(j + 1) / 2] >> 32) : (uint32_t)Ov[(j + 1) / 2];
+      r.v[j] = cc::addc_cc(e, o);
+    }
+    r.v[N - 1] = cc::addc((uint32_t)(Ev[NW - 1] >> 32), 0u);
     final_sub(r.v);
     return r;
   }

@@ -1,0 +1,8 @@
+// Bn254 instantiation of the MSM back end (see msm_curve.cuh).
+#include "msm_curve.cuh"
+
+namespace bz {
+template <>
+const uint32_t* CurveLaunch<Bn254>::fr_mod_host() { return FR254_MOD_H; }
+const CurveOps* curve_ops_bn254() { return CurveLaunch<Bn254>::ops(); }
+}  // namespace bz

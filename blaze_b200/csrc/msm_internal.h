@@ -1,0 +1,80 @@
+// Internal (non-ABI) declarations shared by the MSM translation units.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+
+namespace bz {
+
+// device-side error flags (written with atomicExch into MsmWorkspace::err)
+enum : int {
+  BZ_ERR_NONE = 0,
+  BZ_ERR_SCALAR_RANGE = 1,   // a scalar was not canonical (>= r) / top digit overflow
+};
+
+struct DigitConst {
+  uint32_t K[9];      // sum of the half-window offsets (see k_digits)
+  uint32_t mod[8];    // scalar-field modulus, for the canonical-scalar check
+  int check_mod;
+};
+
+// Everything the kernels need to know about one MSM launch.
+struct MsmPlan {
+  uint64_t M;              // number of (sub)scalars == number of table points used
+  int words_per_scalar;    // 8: full 256-bit scalars; 1: 32-bit limbs against a x8 precomputed table
+  int c;                   // window bits
+  int W;                   // number of windows
+  uint32_t nb;             // buckets per window = 2^(c-1) + 1 (bucket 0 is never accumulated)
+  int fbits;               // level-2 (fine) sort bits
+  int ncoarse;             // level-1 bins = ((nb-1) >> fbits) + 1
+  uint32_t tile, ntiles;   // level-1 tile size / count
+  uint32_t seg_len;        // sorted entries per accumulate thread
+  uint64_t nseg;           // number of accumulate segments = ceil(W*M / seg_len)
+  uint32_t chunk;          // buckets per reduce thread (power of two, divides nb-1)
+  uint32_t nchunks;        // (nb-1) / chunk
+  DigitConst dc;
+};
+
+struct MsmWorkspace {
+  uint32_t* dig;       // [W][M]
+  uint32_t* hmat;      // [W][ntiles][ncoarse]
+  uint32_t* tot;       // [W][ncoarse]
+  uint32_t* base1;     // [W][ncoarse+1]
+  uint2* l1;           // [W][M]
+  uint32_t* sorted;    // [W*M]
+  uint32_t* goff;      // [W*nb + 1]
+  void* buckets;       // [W*nb] XYZZ
+  uint32_t* part_id;   // [nseg][2]
+  void* part_pt;       // [nseg][2] XYZZ
+  void* red_a;         // [W*nchunks] XYZZ (reduce scratch)
+  void* red_b;         // [W*nchunks/..] XYZZ
+  int* err;            // device error flag
+  uint8_t* result;     // 3*FQ_BYTES result record (device)
+  cudaEvent_t ev_acc0, ev_acc1;   // bracket the accumulate kernel alone (roofline timing); may be null
+};
+
+void launch_msm_sort(const MsmPlan& p, const MsmWorkspace& ws, const uint32_t* scalars_dev, cudaStream_t st);
+
+// Per-curve kernels live in msm_curve_*.cu; the engine reaches them through this table.
+struct CurveOps {
+  int code;              // 0 BLS12_377, 1 BN254, 2 BLS12_381 (reference: msm_api.rs:359-364)
+  int fq_bytes;          // 48 / 32
+  int scalar_bits;       // 253 / 254 / 255
+  const uint32_t* fr_mod;   // 8 limbs, host copy
+  size_t affine_bytes;   // Montgomery affine table entry
+  size_t xyzz_bytes;
+  void (*points_to_mont)(const uint8_t* raw, void* table, uint64_t n, cudaStream_t st);
+  void (*bucket_phase)(const MsmPlan& p, const MsmWorkspace& ws, const void* table, cudaStream_t st);
+  // sum `n` canonical result records (Z||Y||X) into one canonical record (multi-GPU combine)
+  void (*combine_results)(const uint8_t* recs, int n, uint8_t* out, cudaStream_t st);
+  // test / bench helpers
+  void (*gen_chain_points)(const uint8_t* p0q_raw, uint64_t first, uint64_t n, uint8_t* out_raw, cudaStream_t st);
+  void (*field_selftest)(const uint8_t* a, const uint8_t* b, uint8_t* out, int n, int op, cudaStream_t st);
+};
+
+const CurveOps* curve_ops_bls12_377();
+const CurveOps* curve_ops_bn254();
+const CurveOps* curve_ops_bls12_381();
+
+}  // namespace bz

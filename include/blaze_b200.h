@@ -1,0 +1,138 @@
+/* blaze_b200 -- C ABI of the B200-native drop-in for ingonyama-zk/blaze's primitive clients.
+ *
+ * Every entry point below replaces one method of the reference's Rust surface
+ * (`DriverClient`, `DriverPrimitive<T,P,I,O>` as implemented by `MSMClient`, `NTTClient`,
+ * `PoseidonClient`); the reference file:line each one stands for is cited next to it.
+ * INTEGRATION.md shows the Rust `extern "C"` block and the `impl DriverPrimitive` a blaze
+ * maintainer would add on top of this header.
+ *
+ * Conventions
+ *   - opaque handles, plain pointers and sizes, no C++/torch types;
+ *   - return value: 0 (BZ_OK) or a negative bz_status that maps 1:1 onto the reference's
+ *     `DriverClientError` variants (/root/reference/src/error.rs:6-32); nothing panics or aborts
+ *     across the ABI (the reference `unwrap()`s / `todo!()`s in several places -- those become
+ *     BZ_ERR_INVALID_PRIMITIVE_PARAM here);
+ *   - `bz_last_error()` returns a thread-local human-readable message for the last failure;
+ *   - the caller owns every buffer; inputs are copied (or consumed by the device) before the
+ *     call returns, matching the reference's move-in `Vec<u8>` semantics (msm_api.rs:28-32);
+ *   - all data is byte-exact wire format: 32-byte little-endian canonical scalars, affine
+ *     x||y little-endian canonical bases (x8 with `2^(32 i) P` when precomputed), Z||Y||X results
+ *     (/root/reference/tests/msm/mod.rs:331-332, 360-380, 397-403).
+ *   - there is NO CPU fallback: without a CUDA device every constructor returns
+ *     BZ_ERR_NO_DEVICE.
+ */
+#ifndef BLAZE_B200_H
+#define BLAZE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum bz_status {
+  BZ_OK = 0,
+  BZ_ERR_WRITE = -1,                   /* DriverClientError::WriteError            error.rs:8-13  */
+  BZ_ERR_READ = -2,                    /* DriverClientError::ReadError             error.rs:14-19 */
+  BZ_ERR_HBICAP_NOT_READY = -3,        /* DriverClientError::HBICAPNotReady        error.rs:20-21 */
+  BZ_ERR_INVALID_PRIMITIVE_PARAM = -4, /* DriverClientError::InvalidPrimitiveParam error.rs:22-23 */
+  BZ_ERR_CSV = -5,                     /* DriverClientError::CsvError              error.rs:24-25 */
+  BZ_ERR_LOAD_FAILED = -6,             /* DriverClientError::LoadFailed            error.rs:26-27 */
+  BZ_ERR_FILE = -7,                    /* DriverClientError::FileError             error.rs:28-29 */
+  BZ_ERR_UNKNOWN = -8,                 /* DriverClientError::Unknown               error.rs:30-31 */
+  BZ_ERR_NO_DEVICE = -9,               /* no usable CUDA device (the reference panics in open_channel, utils.rs:74) */
+  BZ_ERR_NO_RESULT = -10               /* result()/wait_result() with an empty task queue */
+} bz_status;
+
+/* Curve (msm_cfg.rs:4-8); numeric codes follow the image-parameter word (msm_api.rs:359-364). */
+typedef enum bz_curve { BZ_CURVE_BLS377 = 0, BZ_CURVE_BN254 = 1, BZ_CURVE_BLS381 = 2 } bz_curve;
+/* PointMemoryType (msm_cfg.rs:10-14) */
+typedef enum bz_point_memory_type { BZ_MEM_HBM = 0, BZ_MEM_DMA = 1 } bz_point_memory_type;
+/* CardType (dclient_cfg.rs:1-3) plus the card this library drives */
+typedef enum bz_card_type { BZ_CARD_C1100 = 0, BZ_CARD_B200 = 1 } bz_card_type;
+
+typedef struct bz_dclient bz_dclient;
+typedef struct bz_msm bz_msm;
+typedef struct bz_ntt bz_ntt;
+typedef struct bz_poseidon bz_poseidon;
+
+const char* bz_last_error(void);
+/* library / build identification: "blaze_b200 <version> sm_100a" */
+const char* bz_version(void);
+
+/* ------------------------------------------------------------------ DriverClient
+ * `id` is the reference's FPGA slot string (dclient.rs:79-86, env ID) = CUDA device ordinal. */
+int32_t bz_dclient_new(const char* id, int32_t card_type, bz_dclient** out);          /* dclient.rs:79-86   */
+int32_t bz_dclient_free(bz_dclient* dc);
+int32_t bz_dclient_reset(bz_dclient* dc);                                              /* dclient.rs:88-93   */
+/* flat card address space (dclient.rs:456-517): bytes land in / come from the device arena */
+int32_t bz_dclient_dma_write(bz_dclient* dc, uint64_t base, uint64_t offset, const uint8_t* data, size_t len);
+int32_t bz_dclient_dma_read(bz_dclient* dc, uint64_t base, uint64_t offset, uint8_t* out, size_t len);
+/* FPGA-shell management calls the reference's tests make (integration_msm.rs:41-49); there is no
+ * bitstream or AXI firewall on a GPU, so these validate the handle and report "healthy". */
+int32_t bz_dclient_firewalls_status(bz_dclient* dc, uint32_t* blocked_mask);           /* dclient.rs:566-579 */
+int32_t bz_dclient_unblock_firewalls(bz_dclient* dc);                                  /* dclient.rs:258-279 */
+int32_t bz_dclient_initialize_cms(bz_dclient* dc);                                     /* dclient.rs:115-131 */
+int32_t bz_dclient_reset_sensor_data(bz_dclient* dc);                                  /* dclient.rs:133-151 */
+int32_t bz_dclient_setup_before_load_binary(bz_dclient* dc);                           /* dclient.rs:176-187 */
+int32_t bz_dclient_load_binary(bz_dclient* dc, const uint8_t* image, size_t len);      /* dclient.rs:213-236 */
+/* device introspection (B200 addition): name into buf, total/free HBM bytes */
+int32_t bz_dclient_device_info(bz_dclient* dc, char* name, size_t name_len, uint64_t* hbm_total, uint64_t* hbm_free);
+
+/* pinned host memory for callers that want full-rate H2D (B200 addition; optional) */
+int32_t bz_host_alloc(size_t bytes, void** out);
+int32_t bz_host_free(void* p);
+
+/* ------------------------------------------------------------------ MSMClient (src/ingo_msm/msm_api.rs)
+ * Sizes: scalar 32 B; point 96 B (BLS) / 64 B (BN254); result 144 B / 96 B (msm_cfg.rs:44-92). */
+int32_t bz_msm_new(bz_dclient* dc, int32_t curve, int32_t mem_type, int32_t is_precompute, bz_msm** out); /* :44-55 */
+int32_t bz_msm_free(bz_msm* m);
+int32_t bz_msm_loaded_binary_parameters(bz_msm* m, uint32_t out[2]);                   /* :57-70, 333-364 */
+/* MSMParams{nof_elements, hbm_point_addr: Option<(u64,u64)>} (:22-26) */
+int32_t bz_msm_initialize(bz_msm* m, uint32_t nof_elements, int32_t has_hbm_addr, uint64_t hbm_addr,
+                          uint64_t hbm_offset);                                          /* :72-111  */
+int32_t bz_msm_start_process(bz_msm* m);                                                /* :113-120 */
+/* MSMInput{points: Option<Vec<u8>>, scalars, params} (:28-32); points == NULL means None */
+int32_t bz_msm_set_data(bz_msm* m, const uint8_t* points, size_t points_len, const uint8_t* scalars,
+                        size_t scalars_len, uint32_t nof_elements, int32_t has_hbm_addr, uint64_t hbm_addr,
+                        uint64_t hbm_offset);                                            /* :155-220 */
+int32_t bz_msm_wait_result(bz_msm* m);                                                  /* :222-238 */
+/* MSMResult{result, result_label} (:33-37); pops the result queue like POP_RESULT (:265-269) */
+int32_t bz_msm_result(bz_msm* m, uint8_t* out, size_t out_len, uint32_t* result_label);  /* :240-274 */
+int32_t bz_msm_task_label(bz_msm* m, uint32_t* label);                                  /* :278-283 */
+int32_t bz_msm_nof_elements(bz_msm* m, uint32_t* n);                                    /* :285-290 */
+int32_t bz_msm_is_msm_engine_ready(bz_msm* m, uint32_t* ready);                         /* :292-297 */
+int32_t bz_msm_load_data_to_hbm(bz_msm* m, const uint8_t* points, size_t len, uint64_t addr, uint64_t offset); /* :299-313 */
+int32_t bz_msm_get_data_from_hbm(bz_msm* m, uint8_t* out, size_t len, uint64_t addr, uint64_t offset);         /* :315-322 */
+/* wire sizes of this client's curve (msm_cfg.rs:17-29) */
+int32_t bz_msm_sizes(bz_msm* m, uint32_t* scalar_size, uint32_t* point_size, uint32_t* result_point_size,
+                     uint32_t* precompute_factor);
+
+/* --- B200 additions (not in the reference) ---
+ * phase timers, the analogue of the core's per-phase clock counters (msm_hw_code.rs:33-54, get_api
+ * :324-330): milliseconds of the last completed task, measured with CUDA events on the client's stream:
+ * [0] total, [1] ingest+digits+sort, [2] bucket accumulation kernel, [3] merge+reduce+finish */
+int32_t bz_msm_phase_times(bz_msm* m, float ms[4]);
+/* override the window size chosen by the cost model (0 = automatic) */
+int32_t bz_msm_set_window_bits(bz_msm* m, int32_t c);
+/* plan of the last launched task: c, W, buckets/window, segment length */
+int32_t bz_msm_plan_info(bz_msm* m, uint32_t out[4]);
+/* like set_data(points=None) but the scalars already live in device memory (device pointer) */
+int32_t bz_msm_set_scalars_device(bz_msm* m, uint64_t scalars_dev_ptr, uint32_t nof_elements, int32_t has_hbm_addr,
+                                  uint64_t hbm_addr, uint64_t hbm_offset);
+/* sum `n` result records (host memory, result_point_size each) on the device into one canonical
+ * record: the final exchange step of a point-sharded multi-GPU MSM */
+int32_t bz_msm_combine_results(bz_msm* m, const uint8_t* records, int32_t n, uint8_t* out, size_t out_len);
+/* synthetic-input helper: writes points P0 + (first+i)*Q, i in [0,n), in wire format (factor 1)
+ * into the card address space at addr+offset; p0q = P0 || Q in wire format */
+int32_t bz_msm_generate_chain_points(bz_msm* m, const uint8_t* p0q, size_t p0q_len, uint64_t first, uint64_t n,
+                                     uint64_t addr, uint64_t offset);
+/* device self-test of the base-field arithmetic: out[i] = a[i] (op) b[i], canonical LE elements;
+ * op: 0 mul, 1 add, 2 sub, 3 sqr, 4 inv, 5 neg */
+int32_t bz_msm_field_selftest(bz_msm* m, const uint8_t* a, const uint8_t* b, uint8_t* out, int32_t n, int32_t op);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BLAZE_B200_H */

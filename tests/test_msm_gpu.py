@@ -1,0 +1,240 @@
+"""MSM parity on the GPU, through the C ABI (blaze_b200 Python mirror -> libblaze_b200.so).
+
+Mirrors the call order of the reference's integration tests
+(/root/reference/tests/integration_msm.rs:150-207: initialize -> start_process -> set_data ->
+wait_result -> result) and checks what they check (result equals the expected MSM value,
+tests/msm/mod.rs:382-420) -- but bit-exactly against the oracle on seeded inputs.
+"""
+import numpy as np
+import pytest
+
+import blaze_b200 as bz
+from blaze_b200 import Curve, MSMClient, MSMInit, MSMInput, MSMParams, PointMemoryType
+
+from util import CURVE_BY_NAME, chain_points, precompute_bases, random_scalars, tile
+
+pytestmark = pytest.mark.gpu
+
+CURVES = [("BLS12_381", Curve.BLS381), ("BLS12_377", Curve.BLS377), ("BN254", Curve.BN254)]
+
+
+def run_dma(dclient, curve, points, scalars, n, precompute=False, c=0):
+    m = MSMClient.new(MSMInit(PointMemoryType.DMA, precompute, curve), dclient)
+    try:
+        if c:
+            m.set_window_bits(c)
+        params = MSMParams(n, None)
+        m.initialize(params)
+        m.start_process()
+        m.set_data(MSMInput(points, scalars, params))
+        m.wait_result()
+        r = m.result()
+        return r.result, r.result_label, m.plan_info()
+    finally:
+        m.close()
+
+
+@pytest.mark.parametrize("cname,curve", CURVES)
+def test_field_selftest(dclient, oracle, cname, curve):
+    c = CURVE_BY_NAME[cname]
+    rng = np.random.default_rng(5)
+    n = 64
+    vals = [int.from_bytes(rng.bytes(c.fq_bytes), "little") % c.q for _ in range(2 * n)]
+    vals[0:6] = [0, 1, c.q - 1, c.q - 2, 2, c.q >> 1]
+    a = b"".join(v.to_bytes(c.fq_bytes, "little") for v in vals[:n])
+    b = b"".join(v.to_bytes(c.fq_bytes, "little") for v in vals[n:])
+    m = MSMClient.new(MSMInit(PointMemoryType.DMA, False, curve), dclient)
+    try:
+        ops = {0: lambda x, y: x * y % c.q, 1: lambda x, y: (x + y) % c.q, 2: lambda x, y: (x - y) % c.q,
+               3: lambda x, y: x * x % c.q, 5: lambda x, y: (-x) % c.q,
+               4: lambda x, y: pow(x, -1, c.q) if x else 0}
+        for op, fn in ops.items():
+            out = m.field_selftest(a, b, n, op)
+            for i in range(n):
+                got = int.from_bytes(out[i * c.fq_bytes:(i + 1) * c.fq_bytes], "little")
+                assert got == fn(vals[i], vals[n + i]), (cname, op, i)
+    finally:
+        m.close()
+
+
+@pytest.mark.parametrize("cname,curve", CURVES)
+@pytest.mark.parametrize("n", [1, 2, 33, 1000, 1 << 12])
+def test_msm_dma_vs_oracle(dclient, oracle, cname, curve, n):
+    c = CURVE_BY_NAME[cname]
+    pts, _, _ = chain_points(c, n, seed=n)
+    sc = random_scalars(c, n, seed=100 + n)
+    got, label, plan = run_dma(dclient, curve, pts, sc, n)
+    exp = oracle.msm_pippenger(cname, pts, sc, n)
+    assert got == exp, (cname, n, plan)
+
+
+@pytest.mark.parametrize("c_bits", [4, 7, 11, 16])
+def test_msm_window_sizes(dclient, oracle, c_bits):
+    c = CURVE_BY_NAME["BLS12_381"]
+    n = 3000
+    pts, _, _ = chain_points(c, n, seed=3)
+    sc = random_scalars(c, n, seed=4)
+    got, _, plan = run_dma(dclient, Curve.BLS381, pts, sc, n, c=c_bits)
+    assert plan["c"] == c_bits
+    assert got == oracle.msm_pippenger("BLS12_381", pts, sc, n)
+
+
+def test_msm_edge_scalars(dclient, oracle):
+    """0, 1, r-1, powers of two, all-ones digits: exercises digit carries and the top window."""
+    c = CURVE_BY_NAME["BLS12_381"]
+    special = [0, 1, 2, c.r - 1, c.r - 2, (1 << 254), (1 << 255) % c.r, (1 << 128) - 1, 0x8000, 0x7fff, 0xffff,
+               (c.r - 1) // 2, (c.r + 1) // 2]
+    n = len(special)
+    pts, _, _ = chain_points(c, n, seed=9)
+    sc = np.frombuffer(b"".join(int(s).to_bytes(32, "little") for s in special), dtype=np.uint8).copy()
+    for cb in (0, 5, 16):
+        got, _, _ = run_dma(dclient, Curve.BLS381, pts, sc, n, c=cb)
+        assert got == oracle.msm_naive("BLS12_381", bytes(pts), bytes(sc), n, 1)
+
+
+def test_msm_result_infinity(dclient):
+    c = CURVE_BY_NAME["BLS12_381"]
+    n = 4
+    pts, _, _ = chain_points(c, n, seed=1)
+    sc = np.zeros(n * 32, dtype=np.uint8)
+    got, _, _ = run_dma(dclient, Curve.BLS381, pts, sc, n)
+    assert got == (0).to_bytes(48, "little") + (1).to_bytes(48, "little") + (0).to_bytes(48, "little")
+
+
+def test_msm_cancellation_and_duplicates(dclient, oracle):
+    """P and -P and repeated points in one bucket: complete addition (doubling / inverse)."""
+    c = CURVE_BY_NAME["BLS12_381"]
+    base, _, _ = chain_points(c, 4, seed=2)
+    ps = c.point_size
+    p = bytes(base[:ps])
+    x, y = p[:48], int.from_bytes(p[48:], "little")
+    negp = x + ((c.q - y) % c.q).to_bytes(48, "little")
+    pts = np.frombuffer(p + negp + p + p + p + bytes(base[ps:2 * ps]), dtype=np.uint8).copy()
+    s = 0x1234567
+    sc = np.frombuffer(b"".join(int(v).to_bytes(32, "little") for v in [s, s, s, s, s, 5]), dtype=np.uint8).copy()
+    got, _, _ = run_dma(dclient, Curve.BLS381, pts, sc, 6)
+    assert got == oracle.msm_naive("BLS12_381", bytes(pts), bytes(sc), 6, 1)
+
+
+@pytest.mark.parametrize("cname,curve", CURVES)
+def test_msm_reference_tiled_distribution(dclient, oracle, cname, curve):
+    """The reference's own large-input shape: 256 random pairs tiled to n (tests/msm/mod.rs:21-31,
+    92-109): every bucket holds many copies of the same point."""
+    c = CURVE_BY_NAME[cname]
+    n = 256 * 37 + 19
+    pts256, _, _ = chain_points(c, 256, seed=11)
+    sc256 = random_scalars(c, 256, seed=12)
+    pts = tile(pts256, c.point_size, 256, n)
+    sc = tile(sc256, 32, 256, n)
+    got, _, _ = run_dma(dclient, curve, pts, sc, n)
+    assert got == oracle.msm_pippenger(cname, pts, sc, n)
+
+
+@pytest.mark.parametrize("cname,curve", [("BLS12_381", Curve.BLS381), ("BN254", Curve.BN254)])
+def test_msm_precompute_factor8(dclient, oracle, cname, curve):
+    """x8 precomputed bases (tests/msm/mod.rs:360-380): the core pairs 32-bit scalar limbs with
+    the stored 2^(32 i) P; the result must equal the plain MSM."""
+    c = CURVE_BY_NAME[cname]
+    n = 300
+    pts, _, _ = chain_points(c, n, seed=21)
+    sc = random_scalars(c, n, seed=22)
+    bases8 = precompute_bases(c, pts, n, 8)
+    got, _, plan = run_dma(dclient, curve, bases8, sc, n, precompute=True)
+    assert got == oracle.msm_pippenger(cname, pts, sc, n)
+    assert got == oracle.msm_naive(cname, bytes(bases8), bytes(sc), n, 8)
+
+
+def test_msm_hbm_mode_and_labels(dclient, oracle):
+    """integration_msm_hbm.rs:121-226 call order: load points once, then scalars-only tasks;
+    get_data_from_hbm returns the bytes written; labels increase per task."""
+    c = CURVE_BY_NAME["BLS12_381"]
+    n = 2048 + 77
+    pts, p0, q = chain_points(c, n, seed=31)
+    addr, off = 0x0, 0x0
+    m = MSMClient.new(MSMInit(PointMemoryType.HBM, False, Curve.BLS381), dclient)
+    try:
+        params = MSMParams(n, (addr, off))
+        m.load_data_to_hbm(pts, addr, off)
+        assert m.get_data_from_hbm(len(pts), addr, off) == bytes(pts)
+        labels = []
+        for it in range(3):
+            sc = random_scalars(c, n, seed=40 + it)
+            m.initialize(params)
+            m.start_process()
+            m.set_data(MSMInput(None, sc, params))
+            m.wait_result()
+            r = m.result()
+            labels.append(r.result_label)
+            assert r.result == oracle.chain_expected("BLS12_381", p0, q, sc, n)
+        assert labels == sorted(labels) and len(set(labels)) == 3
+        assert m.nof_elements() == n
+        assert m.is_msm_engine_ready() == 1
+        # (points, hbm addr) mode: preload + compute in one call (msm_api.rs:203-216)
+        sc = random_scalars(c, n, seed=50)
+        m.start_process()
+        m.set_data(MSMInput(pts, sc, MSMParams(n, (0x1000000, 0))))
+        m.wait_result()
+        assert m.result().result == oracle.chain_expected("BLS12_381", p0, q, sc, n)
+    finally:
+        m.close()
+
+
+def test_msm_device_generator_matches_oracle(dclient, oracle):
+    c = CURVE_BY_NAME["BLS12_381"]
+    n = 1000
+    pts, p0, q = chain_points(c, n, seed=61)
+    m = MSMClient.new(MSMInit(PointMemoryType.HBM, False, Curve.BLS381), dclient)
+    try:
+        m.generate_chain_points(p0 + q, 0, n, 0x2000000, 0)
+        assert m.get_data_from_hbm(n * 96, 0x2000000, 0) == bytes(pts)
+    finally:
+        m.close()
+
+
+def test_msm_errors(dclient):
+    c = CURVE_BY_NAME["BLS12_381"]
+    m = MSMClient.new(MSMInit(PointMemoryType.HBM, False, Curve.BLS381), dclient)
+    try:
+        with pytest.raises(bz.error.InvalidPrimitiveParam):
+            m.initialize(MSMParams(16, None))          # HBM without an address: the reference panics
+        with pytest.raises(bz.error.NoResult):
+            m.wait_result()
+        pts, _, _ = chain_points(c, 4, seed=1)
+        with pytest.raises(bz.error.InvalidPrimitiveParam):
+            m.set_data(MSMInput(pts, np.zeros(3 * 32, dtype=np.uint8), MSMParams(4, (0, 0))))   # short scalars
+        # non-canonical scalar (>= r) is reported, not silently reduced
+        bad = np.full(4 * 32, 0xff, dtype=np.uint8)
+        m.initialize(MSMParams(4, (0, 0)))
+        m.start_process()
+        m.set_data(MSMInput(pts, bad, MSMParams(4, (0, 0))))
+        with pytest.raises(bz.error.InvalidPrimitiveParam):
+            m.wait_result()
+        with pytest.raises(bz.error.InvalidPrimitiveParam):
+            m.result()
+    finally:
+        m.close()
+
+
+@pytest.mark.parametrize("log_n", [16, 20])
+def test_msm_large_closed_form(dclient, oracle, log_n):
+    """Config 1 size (2^16) vs the full oracle, and 2^20 vs the closed form of the chain workload."""
+    c = CURVE_BY_NAME["BLS12_381"]
+    n = 1 << log_n
+    m = MSMClient.new(MSMInit(PointMemoryType.HBM, False, Curve.BLS381), dclient)
+    try:
+        from util import seed_points
+        p0, q = seed_points(c, 71)
+        m.generate_chain_points(p0 + q, 0, n, 0, 0)
+        sc = random_scalars(c, n, seed=72)
+        params = MSMParams(n, (0, 0))
+        m.initialize(params)
+        m.start_process()
+        m.set_data(MSMInput(None, sc, params))
+        m.wait_result()
+        got = m.result().result
+        assert got == oracle.chain_expected("BLS12_381", p0, q, sc, n)
+        if log_n == 16:
+            pts = np.frombuffer(m.get_data_from_hbm(n * 96, 0, 0), dtype=np.uint8)
+            assert got == oracle.msm_pippenger("BLS12_381", pts, sc, n)
+    finally:
+        m.close()
