@@ -10,4 +10,6 @@ from .driver_client import CardType, DriverClient, DriverConfig, DriverPrimitive
 from .ingo_msm import (Curve, MSMClient, MSMImageParametrs, MSMInit, MSMInput, MSMParams, MSMResult,   # noqa: F401
                        PointMemoryType, PRECOMPUTE_FACTOR, PRECOMPUTE_FACTOR_BASE)
 
+from .ingo_ntt import NTT, NTTClient, NTTInput, NttInit          # noqa: F401
+
 __version__ = "0.1.0"

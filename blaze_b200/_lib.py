@@ -21,6 +21,7 @@ i32, u32, u64, sz = ctypes.c_int32, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_s
 SIGNATURES = {
     "bz_last_error": [],
     "bz_version": [],
+    "bz_kernel_launch_count": [],
     "bz_dclient_new": [ctypes.c_char_p, i32, ctypes.POINTER(vp)],
     "bz_dclient_free": [vp],
     "bz_dclient_reset": [vp],
@@ -56,8 +57,19 @@ SIGNATURES = {
     "bz_msm_combine_results": [vp, vp, i32, vp, sz],
     "bz_msm_generate_chain_points": [vp, vp, sz, u64, u64, u64, u64],
     "bz_msm_field_selftest": [vp, vp, vp, vp, i32, i32],
+    "bz_ntt_new": [vp, i32, ctypes.POINTER(vp)],
+    "bz_ntt_new_ex": [vp, i32, i32, i32, ctypes.POINTER(vp)],
+    "bz_ntt_free": [vp],
+    "bz_ntt_loaded_binary_parameters": [vp, u32p],
+    "bz_ntt_initialize": [vp],
+    "bz_ntt_set_data": [vp, sz, vp, sz],
+    "bz_ntt_start_process": [vp, sz],
+    "bz_ntt_wait_result": [vp],
+    "bz_ntt_result": [vp, sz, vp, sz],
+    "bz_ntt_phase_times": [vp, ctypes.POINTER(ctypes.c_float), u32p],
+    "bz_ntt_slot_device_ptr": [vp, sz, u64p],
 }
-_RESTYPES = {"bz_last_error": ctypes.c_char_p, "bz_version": ctypes.c_char_p}
+_RESTYPES = {"bz_last_error": ctypes.c_char_p, "bz_version": ctypes.c_char_p, "bz_kernel_launch_count": ctypes.c_uint64}
 
 
 def lib():

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "../../include/blaze_b200.h"
+#include "api_common.h"
 #include "msm_internal.h"
 
 using namespace bz;
@@ -27,7 +28,7 @@ using namespace bz;
 // ------------------------------------------------------------------------------------ errors
 static thread_local std::string g_last_error;
 
-static int32_t fail(int32_t code, const char* fmt, ...) {
+int32_t bz_fail(int32_t code, const char* fmt, ...) {
   char buf[512];
   va_list ap;
   va_start(ap, fmt);
@@ -37,12 +38,10 @@ static int32_t fail(int32_t code, const char* fmt, ...) {
   return code;
 }
 
-#define CUDA_TRY(code, expr)                                                                      \
-  do {                                                                                            \
-    cudaError_t _e = (expr);                                                                      \
-    if (_e != cudaSuccess) return fail((code), "%s failed: %s", #expr, cudaGetErrorString(_e));   \
-  } while (0)
+#define fail bz_fail
 
+std::atomic<uint64_t> bz::g_kernel_launches{0};
+extern "C" uint64_t bz_kernel_launch_count(void) { return bz::g_kernel_launches.load(); }
 extern "C" const char* bz_last_error(void) { return g_last_error.c_str(); }
 extern "C" const char* bz_version(void) { return "blaze_b200 0.1.0 sm_100a"; }
 
@@ -63,11 +62,16 @@ struct bz_dclient {
   std::mutex mu;
 };
 
-static int32_t dc_select(bz_dclient* dc) {
+cudaStream_t dc_stream(bz_dclient* dc);
+int dc_device(bz_dclient* dc);
+int32_t dc_select(bz_dclient* dc) {
   if (!dc) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null DriverClient");
   CUDA_TRY(BZ_ERR_NO_DEVICE, cudaSetDevice(dc->device));
   return BZ_OK;
 }
+
+cudaStream_t dc_stream(bz_dclient* dc) { return dc->stream; }
+int dc_device(bz_dclient* dc) { return dc->device; }
 
 static int32_t arena_reserve(bz_dclient* dc, uint64_t end) {
   if (end > ARENA_LIMIT) return fail(BZ_ERR_WRITE, "address 0x%llx beyond the HBM window", (unsigned long long)end);
@@ -118,9 +122,9 @@ extern "C" int32_t bz_dclient_reset(bz_dclient* dc) {
   int32_t rc = dc_select(dc);
   if (rc) return rc;
   std::lock_guard<std::mutex> lk(dc->mu);
+  // The reference toggles the DFX decoupler (dclient.rs:88-93): user logic is reset, HBM contents
+  // survive.  Here: drain the work stream; the arena keeps its bytes.
   CUDA_TRY(BZ_ERR_UNKNOWN, cudaStreamSynchronize(dc->stream));
-  if (dc->arena) CUDA_TRY(BZ_ERR_UNKNOWN, cudaMemsetAsync(dc->arena, 0, dc->arena_cap, dc->stream));
-  dc->epoch++;
   return BZ_OK;
 }
 

@@ -341,6 +341,7 @@ struct CurveLaunch {
   static void points_to_mont(const uint8_t* raw, void* table, uint64_t n, cudaStream_t st) {
     if (!n) return;
     k_points_to_mont<C><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(raw, (AffineM<C>*)table, n);
+    g_kernel_launches += 1;
   }
   static void bucket_phase(const MsmPlan& p, const MsmWorkspace& ws, const void* table, cudaStream_t st) {
     const uint64_t total = (uint64_t)p.W * p.M;
@@ -360,8 +361,10 @@ struct CurveLaunch {
     XyzzM<C>* b = (XyzzM<C>*)ws.red_b;
     k_reduce_chunks<C><<<(n + 127) / 128, 128, 0, st>>>(buckets, a, p.nb, p.chunk, p.nchunks, p.W);
     // tree-sum the chunk results of each window down to one point per window
+    g_kernel_launches += 4;   // accumulate, merge, reduce_chunks, finish
     uint32_t per = p.nchunks;
     while (per > 1) {
+      g_kernel_launches += 1;
       uint32_t group = per > 64 ? 64 : per;
       while (per % group) group--;   // per is a power of two, so this never iterates
       uint32_t nper = per / group;

@@ -5,7 +5,12 @@
 #include <cstddef>
 #include <cstdint>
 
+#include <atomic>
+
 namespace bz {
+
+// number of kernels this library has launched in this process (bz_kernel_launch_count)
+extern std::atomic<uint64_t> g_kernel_launches;
 
 // device-side error flags (written with atomicExch into MsmWorkspace::err)
 enum : int {

@@ -237,6 +237,7 @@ void launch_msm_sort(const MsmPlan& p, const MsmWorkspace& ws, const uint32_t* s
   dim3 g2(p.ncoarse, p.W);
   size_t sh2 = ((size_t)(1u << p.fbits) + 256) * sizeof(uint32_t);
   k_sort2<<<g2, 256, sh2, st>>>(ws.l1, M, p.fbits, p.ncoarse, p.nb, p.W, ws.base1, ws.sorted, ws.goff);
+  g_kernel_launches += 6;
 }
 
 }  // namespace bz

@@ -1,0 +1,106 @@
+"""`NTTClient` -- Python mirror of /root/reference/src/ingo_ntt/ntt_api.rs over the C ABI.
+
+    NTTClient.new(NTT.Ntt, dclient)                              ntt_api.rs:26-31 (2^27, BLS12-381 Fr)
+    set_data(NTTInput{buf_host, data}) / initialize(NttInit{}) / start_process(Some(buf_kernel))
+    / wait_result() / result(Some(buf))                          ntt_api.rs:37-124
+`NTTClient.new_ex(...)` is the B200 addition for other sizes / fields / the inverse transform.
+"""
+import ctypes
+import enum
+from dataclasses import dataclass
+
+from ._lib import lib, buf_ptr
+from .driver_client import DriverClient, DriverPrimitive
+from .error import check
+
+
+class NTT(enum.IntEnum):       # ntt_api.rs:8-10
+    Ntt = 0
+
+
+@dataclass
+class NttInit:                 # ntt_api.rs:17
+    pass
+
+
+@dataclass
+class NTTInput:                # ntt_api.rs:19-23
+    buf_host: int
+    data: object
+
+
+class NTTClient(DriverPrimitive):
+    NTT_LOG_SIZE = 27          # ntt_data.rs:65-66
+
+    def __init__(self, ptype=NTT.Ntt, dclient: DriverClient = None, *, field=2, log_size=None, inverse=False):
+        self.driver_client = dclient
+        h = ctypes.c_void_p()
+        if log_size is None:
+            check(lib().bz_ntt_new(dclient._h, int(ptype), ctypes.byref(h)))
+            log_size = self.NTT_LOG_SIZE
+        else:
+            check(lib().bz_ntt_new_ex(dclient._h, int(field), int(log_size), 1 if inverse else 0, ctypes.byref(h)))
+        self._h = h
+        self.log_size = log_size
+        self.nbytes = (1 << log_size) * 32
+
+    @classmethod
+    def new(cls, ptype, dclient):
+        return cls(ptype, dclient)
+
+    @classmethod
+    def new_ex(cls, dclient, field=2, log_size=27, inverse=False):
+        return cls(NTT.Ntt, dclient, field=field, log_size=log_size, inverse=inverse)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().bz_ntt_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def loaded_binary_parameters(self):                       # todo!() in the reference (ntt_api.rs:33-35)
+        out = (ctypes.c_uint32 * 2)()
+        check(lib().bz_ntt_loaded_binary_parameters(self._h, out))
+        return [out[0], out[1]]
+
+    def initialize(self, param=None):                         # ntt_api.rs:37-56
+        check(lib().bz_ntt_initialize(self._h))
+
+    def set_data(self, input: NTTInput):                      # ntt_api.rs:72-87
+        p, n, keep = buf_ptr(input.data)
+        check(lib().bz_ntt_set_data(self._h, int(input.buf_host), p, n))
+
+    def start_process(self, buf_kernel=None):                 # ntt_api.rs:58-70 (unwrap()s None)
+        if buf_kernel is None:
+            from .error import InvalidPrimitiveParam
+            raise InvalidPrimitiveParam("start_process needs Some(buf_kernel)", -4)
+        check(lib().bz_ntt_start_process(self._h, int(buf_kernel)))
+
+    def wait_result(self):                                    # ntt_api.rs:89-108
+        check(lib().bz_ntt_wait_result(self._h))
+
+    def result(self, buf_num=None, out=None):                 # ntt_api.rs:110-124
+        if buf_num is None:
+            from .error import InvalidPrimitiveParam
+            raise InvalidPrimitiveParam("result needs Some(buf_num)", -4)
+        if out is None:
+            out = bytearray(self.nbytes)
+        p, n, keep = buf_ptr(out)
+        check(lib().bz_ntt_result(self._h, int(buf_num), p, n))
+        return out
+
+    # ---- B200 additions
+    def phase_times(self):
+        ms, passes = ctypes.c_float(), ctypes.c_uint32()
+        check(lib().bz_ntt_phase_times(self._h, ctypes.byref(ms), ctypes.byref(passes)))
+        return {"total": ms.value, "passes": passes.value}
+
+    def slot_device_ptr(self, buf_num):
+        v = ctypes.c_uint64()
+        check(lib().bz_ntt_slot_device_ptr(self._h, int(buf_num), ctypes.byref(v)))
+        return v.value

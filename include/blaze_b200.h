@@ -60,6 +60,8 @@ typedef struct bz_poseidon bz_poseidon;
 const char* bz_last_error(void);
 /* library / build identification: "blaze_b200 <version> sm_100a" */
 const char* bz_version(void);
+/* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
+uint64_t bz_kernel_launch_count(void);
 
 /* ------------------------------------------------------------------ DriverClient
  * `id` is the reference's FPGA slot string (dclient.rs:79-86, env ID) = CUDA device ordinal. */
@@ -131,6 +133,28 @@ int32_t bz_msm_generate_chain_points(bz_msm* m, const uint8_t* p0q, size_t p0q_l
 /* device self-test of the base-field arithmetic: out[i] = a[i] (op) b[i], canonical LE elements;
  * op: 0 mul, 1 add, 2 sub, 3 sqr, 4 inv, 5 neg */
 int32_t bz_msm_field_selftest(bz_msm* m, const uint8_t* a, const uint8_t* b, uint8_t* out, int32_t n, int32_t op);
+
+/* ------------------------------------------------------------------ NTTClient (src/ingo_ntt/ntt_api.rs)
+ * I/O: flat vector of 2^log_size field elements, 32 bytes little-endian canonical each
+ * (ntt_api.rs:20-23, README.md:118).  Semantics fixed by BASELINE.json: BLS12-381 Fr, arkworks
+ * Radix2EvaluationDomain::fft -- natural order in and out, out[k] = sum_j in[j] w^(jk).
+ * Two buffer slots (ntt_data.rs:42,54-56); start_process transforms a slot in place. */
+int32_t bz_ntt_new(bz_dclient* dc, int32_t ntt_type /* NTT::Ntt = 0 */, bz_ntt** out);   /* :26-31, size 2^27 */
+int32_t bz_ntt_free(bz_ntt* t);
+int32_t bz_ntt_loaded_binary_parameters(bz_ntt* t, uint32_t out[2]);                     /* :33-35 (todo!() there) */
+int32_t bz_ntt_initialize(bz_ntt* t);                                                     /* :37-56   */
+int32_t bz_ntt_set_data(bz_ntt* t, size_t buf_host, const uint8_t* data, size_t len);     /* :72-87   */
+int32_t bz_ntt_start_process(bz_ntt* t, size_t buf_kernel);                               /* :58-70   */
+int32_t bz_ntt_wait_result(bz_ntt* t);                                                    /* :89-108  */
+int32_t bz_ntt_result(bz_ntt* t, size_t buf_num, uint8_t* out, size_t out_len);           /* :110-124 */
+/* --- B200 additions --- */
+/* any size 2^log_size (<= 2^30 and <= the field's two-adicity), any of the three scalar fields
+ * (bz_curve code), forward or inverse (inverse includes the 1/n scaling) */
+int32_t bz_ntt_new_ex(bz_dclient* dc, int32_t field, int32_t log_size, int32_t inverse, bz_ntt** out);
+/* device time of the last transform (CUDA events on the client's stream) and its number of passes */
+int32_t bz_ntt_phase_times(bz_ntt* t, float* total_ms, uint32_t* passes);
+/* device address of the buffer currently holding slot `buf_num` (device-resident use) */
+int32_t bz_ntt_slot_device_ptr(bz_ntt* t, size_t buf_num, uint64_t* dev_ptr);
 
 #ifdef __cplusplus
 }
