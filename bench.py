@@ -130,6 +130,11 @@ def run_reference(args, rank, world):
     for _ in range(max(1, min(args.warmup, 1))):
         cpu_port_rate(min(ln, 14))
     rates, times = [], []
+    # bounded sample per step: size it so that K steps take a couple of minutes at most on this box
+    r0, th, dt0 = cpu_port_rate(16)
+    budget = 120.0 / max(1, args.steps + 1)
+    while ln < 24 and (1 << (ln + 1)) / r0 < budget:
+        ln += 1
     for s in range(args.steps):
         r, th, dt = cpu_port_rate(ln, seed=900 + s)
         rates.append(r)
@@ -322,7 +327,13 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             from oracle import capi
             capi.build()
-            r, th, dt = cpu_port_rate(args.cpu_sample_log_n)
+            # bounded sample: aim at 10-30 s of CPU work on this box (probe at 2^16, then size it)
+            r0, th, dt0 = cpu_port_rate(16)
+            ln = args.cpu_sample_log_n
+            while ln < 24 and (1 << (ln + 1)) / r0 < 20.0:
+                ln += 1
+            args.cpu_sample_log_n = ln
+            r, th, dt = cpu_port_rate(ln)
             line["cpu_baseline"] = {"value": r, "unit": UNIT, "cores": th, "kind": "port",
                                     "sample": "one 2^%d-point prefix of the workload, %.1f s (oracle: arkworks-0.3-style "
                                               "Pippenger, C++)" % (args.cpu_sample_log_n, dt)}

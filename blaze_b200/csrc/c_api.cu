@@ -350,7 +350,11 @@ static int32_t make_plan(bz_msm* m, uint64_t M, int words_per_scalar) {
     DigitConst dcx{};
     int W = plan_windows(smax, sbits, c, dcx);
     if ((uint64_t)W * M >= (1ull << 32)) continue;
-    double cost = (double)W * ((double)M + 3.0 * (double)(1ull << (c - 1)));
+    // measured on B200 (perf_probe, 2^24..2^26): per (scalar, window) the sort costs 0.14 of a mixed add
+    // up to c = 20 and about doubles per two extra bits (more coarse bins -> more scattered writes);
+    // the running-sum reduction costs about 6 mixed-add equivalents per bucket
+    double sort_w = c <= 20 ? 0.14 : 0.14 * (1.0 + 0.5 * (c - 20));
+    double cost = (double)W * ((double)M * (1.0 + sort_w) + 6.0 * (double)(1ull << (c - 1)));
     if (cost < best) { best = cost; best_c = c; }
   }
   if (!best_c) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "no feasible window size for %llu elements", (unsigned long long)M);
