@@ -355,13 +355,25 @@ static int32_t make_plan(bz_msm* m, uint64_t M, int words_per_scalar) {
     // the running-sum reduction costs about 6 mixed-add equivalents per bucket
     double sort_w = c <= 20 ? 0.14 : 0.14 * (1.0 + 0.5 * (c - 20));
     double cost = (double)W * ((double)M * (1.0 + sort_w) + 6.0 * (double)(1ull << (c - 1)));
+    // a top window with only a few bits funnels all M entries into a handful of buckets of one
+    // coarse bin (one CTA sorts them, long merge chains): avoid such c unless the problem is tiny
+    int top_bits = sbits - c * (W - 1);
+    if (top_bits < 6 && M > (1u << 16)) cost *= 1.5;
     if (cost < best) { best = cost; best_c = c; }
   }
   if (!best_c) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "no feasible window size for %llu elements", (unsigned long long)M);
   p.c = best_c;
   p.W = plan_windows(smax, sbits, p.c, p.dc);
   p.nb = (1u << (p.c - 1)) + 1;
-  p.fbits = std::min(10, p.c / 2);
+  // level-2 (fine) bits: a coarse bin should hold ~32K entries (measured best at 2^26) so that the CTA that sorts it owns a
+  // small, quickly-filled output window (L2 merges its 4-byte scatter writes into full sectors)
+  {
+    int f = 1;
+    while (f < 10 && f < p.c - 1 && ((double)M / (double)(1ull << (p.c - 1 - (f + 1)))) <= 32768.0) f++;
+    p.fbits = std::max(1, std::min(f, p.c - 1));
+    while (((p.nb - 1) >> p.fbits) + 1 > 8193) p.fbits++;   // level-1 histogram must fit shared memory
+    if (const char* e = getenv("BZ_MSM_FBITS")) { int v = atoi(e); if (v >= 1 && v <= 12 && v < p.c) p.fbits = v; }
+  }
   p.ncoarse = (int)(((p.nb - 1) >> p.fbits) + 1);
   p.tile = 65536;
   p.ntiles = (uint32_t)((M + p.tile - 1) / p.tile);
@@ -372,13 +384,14 @@ static int32_t make_plan(bz_msm* m, uint64_t M, int words_per_scalar) {
   if (const char* e = getenv("BZ_MSM_SEG")) L = (uint32_t)std::max(1, atoi(e));
   p.seg_len = L;
   p.nseg = (total + L - 1) / L;
-  uint32_t nbk = p.nb - 1;
-  p.chunk = std::min<uint32_t>(nbk, 128);
+  // reduction chunk (k_reduce_level): 16 buckets per thread, 8 when that leaves the machine underfilled
+  p.chunk = ((uint64_t)p.W * p.nb / 16 < 148ull * 256) ? 8 : 16;
   if (const char* e = getenv("BZ_MSM_CHUNK")) {
     uint32_t ch = (uint32_t)atoi(e);
-    if (ch && (ch & (ch - 1)) == 0 && ch <= nbk) p.chunk = ch;
+    if (ch >= 2 && (ch & (ch - 1)) == 0 && ch <= 1024) p.chunk = ch;
   }
-  p.nchunks = nbk / p.chunk;
+  p.nchunks = (p.nb + p.chunk - 1) / p.chunk;
+  uint32_t nch1 = (p.nchunks + p.chunk - 1) / p.chunk;
 
   size_t xb = m->ops->xyzz_bytes;
   cudaError_t e = cudaSuccess;
@@ -393,8 +406,15 @@ static int32_t make_plan(bz_msm* m, uint64_t M, int words_per_scalar) {
   A((uint8_t**)&m->ws.buckets, (size_t)p.W * p.nb * xb);
   A(&m->ws.part_id, (size_t)p.nseg * 2 * 4);
   A((uint8_t**)&m->ws.part_pt, (size_t)p.nseg * 2 * xb);
-  A((uint8_t**)&m->ws.red_a, (size_t)p.W * p.nchunks * xb);
-  A((uint8_t**)&m->ws.red_b, (size_t)p.W * std::max<uint32_t>(1, p.nchunks / 2) * xb);
+  {
+    uint64_t n = p.nseg, tot = 0;
+    while (true) { n = (n + MERGE_GROUP - 1) / MERGE_GROUP; tot += n; if (n == 1) break; }
+    A(&m->ws.part2_id, (size_t)tot * 2 * 4);
+    A((uint8_t**)&m->ws.part2_pt, (size_t)tot * 2 * xb);
+  }
+  A(&m->ws.wbase, (size_t)(p.W + 1) * 4);
+  A((uint8_t**)&m->ws.red_a, (size_t)2 * p.W * p.nchunks * xb);        // S and V of the even levels
+  A((uint8_t**)&m->ws.red_b, (size_t)2 * p.W * (nch1 + 1) * xb);       // ... of the odd levels
   A(&m->ws.err, 16);
   A(&m->ws.result, 256);
   if (e != cudaSuccess) {

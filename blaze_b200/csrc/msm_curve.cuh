@@ -123,12 +123,18 @@ template <class C>
 __global__ void __launch_bounds__(128, 2)
 k_accumulate(const AffineM<C>* __restrict__ table, const uint32_t* __restrict__ sorted,
              const uint32_t* __restrict__ goff, XyzzM<C>* __restrict__ buckets, uint32_t* __restrict__ part_id,
-             XyzzM<C>* __restrict__ part_pt, uint64_t total, uint32_t L, uint32_t nb, uint32_t ngoff) {
+             XyzzM<C>* __restrict__ part_pt, uint64_t nseg, uint32_t L, uint32_t nb, uint32_t ngoff) {
   typedef dev<C> D;
   typedef ec<C> G;
   uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nseg) return;
+  const uint64_t total = __ldg(goff + ngoff);   // zero digits are dropped by the sort: data dependent
   uint64_t s64 = t * L;
-  if (s64 >= total) return;
+  if (s64 >= total) {
+    part_id[2 * t] = 0xffffffffu;
+    part_id[2 * t + 1] = 0xffffffffu;
+    return;
+  }
   const uint32_t s = (uint32_t)s64;
   const uint32_t e = (uint32_t)(s64 + L < total ? s64 + L : total);
   // largest g with goff[g] <= s
@@ -174,71 +180,97 @@ k_accumulate(const AffineM<C>* __restrict__ table, const uint32_t* __restrict__ 
   part_id[2 * t + 1] = id1;
 }
 
-// fold the partial sums of buckets that straddle segment boundaries
+// Fold the partial sums of buckets that straddle segment boundaries -- as a tree, so that one
+// bucket holding millions of entries (all scalars equal, or the reference's tiled test vectors) does
+// not serialise on one thread.  Level k: a thread owns `group` consecutive child units (segments at
+// level 1, groups of the level below afterwards), i.e. positions [g*span, (g+1)*span) of the sorted
+// array; it walks the children's (head, tail) partial entries in order, sums equal ids, and flushes
+// a finished run to its bucket if the bucket lies inside the span, else to its own head / tail slot.
+// The top level spans everything, so every remaining run lands in its bucket.
 template <class C>
-__global__ void __launch_bounds__(128) k_merge_partials(const uint32_t* __restrict__ goff,
-                                                        XyzzM<C>* __restrict__ buckets,
-                                                        const uint32_t* __restrict__ part_id,
-                                                        const XyzzM<C>* __restrict__ part_pt, uint64_t nseg,
-                                                        uint32_t L) {
+__global__ void __launch_bounds__(128) k_merge_level(const uint32_t* __restrict__ goff, uint32_t ngoff,
+                                                     XyzzM<C>* __restrict__ buckets,
+                                                     const uint32_t* __restrict__ in_id,
+                                                     const XyzzM<C>* __restrict__ in_pt, uint64_t n_children,
+                                                     uint32_t group, uint64_t span /* positions per group */,
+                                                     uint32_t* __restrict__ out_id, XyzzM<C>* __restrict__ out_pt,
+                                                     uint64_t n_groups) {
   typedef dev<C> D;
   typedef ec<C> G;
-  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nseg) return;
-  uint32_t g = part_id[2 * t + 1];
-  if (g == 0xffffffffu) return;        // runs start at a tail entry
-  XYZZ<C> acc = D::load_xyzz(part_pt + 2 * t + 1);
-  uint32_t bend = goff[g + 1];
-  for (uint64_t u = t + 1; u < nseg; u++) {
-    if (part_id[2 * u] != g) break;
-    XYZZ<C> o = D::load_xyzz(part_pt + 2 * u);
-    G::add(acc, o);
-    if ((uint64_t)bend <= (u + 1) * L) break;   // bucket ends inside segment u
+  uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_groups) return;
+  const uint64_t total = __ldg(goff + ngoff);
+  const uint64_t lo = g * span;
+  uint64_t hi = lo + span;
+  if (hi > total || n_groups == 1) hi = total;
+  uint32_t id0 = 0xffffffffu, id1 = 0xffffffffu;
+  uint32_t cur = 0xffffffffu;
+  XYZZ<C> acc = G::infinity();
+  uint64_t c0 = g * group, c1 = c0 + group;
+  if (c1 > n_children) c1 = n_children;
+  for (uint64_t e = 2 * c0; e <= 2 * c1; e++) {
+    uint32_t id = e < 2 * c1 ? in_id[e] : 0xfffffffeu;   // sentinel flushes the last run
+    if (id == 0xffffffffu) continue;
+    if (id != cur) {
+      if (cur != 0xffffffffu) {
+        bool left_open = (uint64_t)goff[cur] < lo, right_open = (uint64_t)goff[cur + 1] > hi;
+        if (!left_open && !right_open) D::store_xyzz(buckets + cur, acc);
+        else if (left_open) { id0 = cur; D::store_xyzz(out_pt + 2 * g, acc); }
+        else { id1 = cur; D::store_xyzz(out_pt + 2 * g + 1, acc); }
+      }
+      if (id == 0xfffffffeu) break;
+      cur = id;
+      acc = D::load_xyzz(in_pt + e);
+    } else {
+      XYZZ<C> o = D::load_xyzz(in_pt + e);
+      G::add(acc, o);
+    }
   }
-  D::store_xyzz(buckets + g, acc);
+  out_id[2 * g] = id0;
+  out_id[2 * g + 1] = id1;
 }
 
 // ---------------------------------------------------------------------------------------------
-// bucket reduction: per window sum_b b * B_b, buckets 1..nb-1 split into chunks of `chunk`
+// bucket reduction.  Per window we need T = sum_i i * A[i] over the bucket array A[0..n) (bucket 0
+// has weight 0, so it needs no special case).  Chunks of s entries:
+//     T = sum_k R_k + s * sum_k k * S_k,   R_k = sum_{t<s} t * A[ks+t],  S_k = sum_{t<s} A[ks+t]
+// and the second term is the same problem on the array S (one entry per chunk): a recursion of
+// log_s(n) levels, one launch each, every level with thousands of independent running sums.
+// The level results are folded as they go:  V^l_k = s^l * R^l_k + sum_{j in chunk k} V^{l-1}_j,
+// so the window total is the single V of the top level.
 template <class C>
 __global__ void __launch_bounds__(128, 2)
-k_reduce_chunks(const XyzzM<C>* __restrict__ buckets, XyzzM<C>* __restrict__ out, uint32_t nb, uint32_t chunk,
-                uint32_t nchunks, int W) {
+k_reduce_level(const XyzzM<C>* __restrict__ A, const XyzzM<C>* __restrict__ Vin, uint32_t n, uint32_t s,
+               uint32_t nchunks, int W, int level_shift /* l * log2(s) */, XyzzM<C>* __restrict__ Sout,
+               XyzzM<C>* __restrict__ Vout) {
   typedef dev<C> D;
   typedef ec<C> G;
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (uint32_t)W * nchunks) return;
-  uint32_t w = t / nchunks, j = t % nchunks;
-  const XyzzM<C>* B = buckets + (uint64_t)w * nb;
-  uint32_t lo = j * chunk + 1, hi = lo + chunk - 1;
+  uint32_t w = t / nchunks, k = t % nchunks;
+  const XyzzM<C>* a = A + (uint64_t)w * n;
+  uint32_t lo = k * s, hi = lo + s;
+  if (hi > n) hi = n;
   XYZZ<C> S = G::infinity(), R = G::infinity();
-  for (uint32_t b = hi; b >= lo; b--) {
-    XYZZ<C> v = D::load_xyzz(B + b);
+  for (uint32_t i = hi - 1; i > lo; i--) {
+    XYZZ<C> v = D::load_xyzz(a + i);
     G::add(S, v);
     G::add(R, S);
   }
-  // sum_{b in chunk} b*B_b = R + (lo-1)*S
-  if (lo > 1) {
-    XYZZ<C> m = G::mul_small(S, lo - 1);
-    G::add(R, m);
+  {
+    XYZZ<C> v = D::load_xyzz(a + lo);
+    G::add(S, v);
   }
-  D::store_xyzz(out + t, R);
-}
-
-// out[i] = sum_{k<group} in[i*group + k]
-template <class C>
-__global__ void __launch_bounds__(128) k_sum_groups(const XyzzM<C>* __restrict__ in, XyzzM<C>* __restrict__ out,
-                                                    uint32_t nout, uint32_t group) {
-  typedef dev<C> D;
-  typedef ec<C> G;
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nout) return;
-  XYZZ<C> acc = G::infinity();
-  for (uint32_t k = 0; k < group; k++) {
-    XYZZ<C> v = D::load_xyzz(in + (uint64_t)i * group + k);
-    G::add(acc, v);
+  for (int d = 0; d < level_shift; d++) R = G::dbl(R);
+  if (Vin) {
+    const XyzzM<C>* vin = Vin + (uint64_t)w * n;
+    for (uint32_t i = lo; i < hi; i++) {
+      XYZZ<C> v = D::load_xyzz(vin + i);
+      G::add(R, v);
+    }
   }
-  D::store_xyzz(out + i, acc);
+  D::store_xyzz(Sout + t, S);
+  D::store_xyzz(Vout + t, R);
 }
 
 // Horner over the window sums, normalise, serialise
@@ -344,36 +376,63 @@ struct CurveLaunch {
     g_kernel_launches += 1;
   }
   static void bucket_phase(const MsmPlan& p, const MsmWorkspace& ws, const void* table, cudaStream_t st) {
-    const uint64_t total = (uint64_t)p.W * p.M;
     const uint32_t ngoff = (uint32_t)p.W * p.nb;
     XyzzM<C>* buckets = (XyzzM<C>*)ws.buckets;
     cudaMemsetAsync(buckets, 0, (size_t)ngoff * sizeof(XyzzM<C>), st);
     if (ws.ev_acc0) cudaEventRecord(ws.ev_acc0, st);
     k_accumulate<C><<<(unsigned)((p.nseg + 127) / 128), 128, 0, st>>>(
-        (const AffineM<C>*)table, ws.sorted, ws.goff, buckets, ws.part_id, (XyzzM<C>*)ws.part_pt, total, p.seg_len,
+        (const AffineM<C>*)table, ws.sorted, ws.goff, buckets, ws.part_id, (XyzzM<C>*)ws.part_pt, p.nseg, p.seg_len,
         p.nb, ngoff);
     if (ws.ev_acc1) cudaEventRecord(ws.ev_acc1, st);
-    k_merge_partials<C><<<(unsigned)((p.nseg + 127) / 128), 128, 0, st>>>(ws.goff, buckets, ws.part_id,
-                                                                          (const XyzzM<C>*)ws.part_pt, p.nseg,
-                                                                          p.seg_len);
-    uint32_t n = (uint32_t)p.W * p.nchunks;
-    XyzzM<C>* a = (XyzzM<C>*)ws.red_a;
-    XyzzM<C>* b = (XyzzM<C>*)ws.red_b;
-    k_reduce_chunks<C><<<(n + 127) / 128, 128, 0, st>>>(buckets, a, p.nb, p.chunk, p.nchunks, p.W);
-    // tree-sum the chunk results of each window down to one point per window
-    g_kernel_launches += 4;   // accumulate, merge, reduce_chunks, finish
-    uint32_t per = p.nchunks;
-    while (per > 1) {
-      g_kernel_launches += 1;
-      uint32_t group = per > 64 ? 64 : per;
-      while (per % group) group--;   // per is a power of two, so this never iterates
-      uint32_t nper = per / group;
-      uint32_t nout = (uint32_t)p.W * nper;
-      k_sum_groups<C><<<(nout + 127) / 128, 128, 0, st>>>(a, b, nout, group);
-      XyzzM<C>* tmp = a; a = b; b = tmp;
-      per = nper;
+    {
+      // merge tree over the partial list (see k_merge_level)
+      const uint32_t group = MERGE_GROUP;
+      const uint32_t* in_id = ws.part_id;
+      const XyzzM<C>* in_pt = (const XyzzM<C>*)ws.part_pt;
+      uint32_t* out_id = ws.part2_id;
+      XyzzM<C>* out_pt = (XyzzM<C>*)ws.part2_pt;
+      uint64_t n_children = p.nseg, span = (uint64_t)p.seg_len * group;
+      while (true) {
+        uint64_t n_groups = (n_children + group - 1) / group;
+        k_merge_level<C><<<(unsigned)((n_groups + 127) / 128), 128, 0, st>>>(ws.goff, ngoff, buckets, in_id, in_pt,
+                                                                             n_children, group, span, out_id, out_pt,
+                                                                             n_groups);
+        g_kernel_launches += 1;
+        if (n_groups == 1) break;
+        in_id = out_id;
+        in_pt = out_pt;
+        out_id += 2 * n_groups;
+        out_pt += 2 * n_groups;
+        n_children = n_groups;
+        span *= group;
+      }
     }
-    k_finish<C><<<1, 32, 0, st>>>(a, p.W, p.c, ws.result);
+    // multi-level running-sum reduction (see k_reduce_level); scratch: red_a = S / V of even levels, red_b = odd
+    g_kernel_launches += 2;   // accumulate, finish
+    const uint32_t s = p.chunk;
+    int log_s = 0;
+    while ((1u << log_s) < s) log_s++;
+    const XyzzM<C>* A = buckets;
+    const XyzzM<C>* Vin = nullptr;
+    uint32_t n = p.nb;
+    XyzzM<C>* scratch[2] = {(XyzzM<C>*)ws.red_a, (XyzzM<C>*)ws.red_b};
+    int level = 0;
+    const XyzzM<C>* top = nullptr;
+    while (true) {
+      uint32_t nch = (n + s - 1) / s;
+      XyzzM<C>* Sout = scratch[level & 1];
+      XyzzM<C>* Vout = Sout + (size_t)p.W * nch;
+      uint32_t nt = (uint32_t)p.W * nch;
+      k_reduce_level<C><<<(nt + 127) / 128, 128, 0, st>>>(A, Vin, n, s, nch, p.W, level * log_s, Sout, Vout);
+      g_kernel_launches += 1;
+      top = Vout;
+      if (nch == 1) break;
+      A = Sout;
+      Vin = Vout;
+      n = nch;
+      level++;
+    }
+    k_finish<C><<<1, 32, 0, st>>>(top, p.W, p.c, ws.result);
   }
   static void combine_results(const uint8_t* recs, int n, uint8_t* out, cudaStream_t st) {
     k_combine_results<C><<<1, 32, 0, st>>>(recs, n, out);

@@ -18,6 +18,8 @@ enum : int {
   BZ_ERR_SCALAR_RANGE = 1,   // a scalar was not canonical (>= r) / top digit overflow
 };
 
+#define MERGE_GROUP 64   // children per thread in the partial-merge tree
+
 struct DigitConst {
   uint32_t K[9];      // sum of the half-window offsets (see k_digits)
   uint32_t mod[8];    // scalar-field modulus, for the canonical-scalar check
@@ -36,8 +38,8 @@ struct MsmPlan {
   uint32_t tile, ntiles;   // level-1 tile size / count
   uint32_t seg_len;        // sorted entries per accumulate thread
   uint64_t nseg;           // number of accumulate segments = ceil(W*M / seg_len)
-  uint32_t chunk;          // buckets per reduce thread (power of two, divides nb-1)
-  uint32_t nchunks;        // (nb-1) / chunk
+  uint32_t chunk;          // entries per reduce thread at every level of the running-sum recursion (power of two)
+  uint32_t nchunks;        // ceil(nb / chunk): level-0 chunk count
   DigitConst dc;
 };
 
@@ -46,14 +48,17 @@ struct MsmWorkspace {
   uint32_t* hmat;      // [W][ntiles][ncoarse]
   uint32_t* tot;       // [W][ncoarse]
   uint32_t* base1;     // [W][ncoarse+1]
+  uint32_t* wbase;     // [W+1] start of each window in `sorted` (zero digits are dropped)
   uint2* l1;           // [W][M]
   uint32_t* sorted;    // [W*M]
   uint32_t* goff;      // [W*nb + 1]
   void* buckets;       // [W*nb] XYZZ
   uint32_t* part_id;   // [nseg][2]
   void* part_pt;       // [nseg][2] XYZZ
-  void* red_a;         // [W*nchunks] XYZZ (reduce scratch)
-  void* red_b;         // [W*nchunks/..] XYZZ
+  uint32_t* part2_id;  // merge-tree levels above the segments: [sum_k ceil(nseg / MERGE_GROUP^k)][2]
+  void* part2_pt;
+  void* red_a;         // [2][W*nchunks] XYZZ: S and V outputs of the even reduction levels
+  void* red_b;         // ... of the odd levels
   int* err;            // device error flag
   uint8_t* result;     // 3*FQ_BYTES result record (device)
   cudaEvent_t ev_acc0, ev_acc1;   // bracket the accumulate kernel alone (roofline timing); may be null

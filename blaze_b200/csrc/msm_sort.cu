@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(512) k_hist1(const uint32_t* __restrict__ dig,
   const uint32_t* d = dig + (uint64_t)w * M;
   for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
     uint32_t b = __ldg(d + i) & 0x7fffffffu;
-    atomicAdd(&sh[b >> fbits], 1u);
+    if (b) atomicAdd(&sh[b >> fbits], 1u);   // zero digits contribute nothing: dropped here
   }
   __syncthreads();
   uint32_t* out = hmat + ((uint64_t)w * ntiles + t) * ncoarse;
@@ -145,6 +145,19 @@ __global__ void __launch_bounds__(1024) k_binscan1(const uint32_t* __restrict__ 
   if (threadIdx.x == blockDim.x - 1) b[ncoarse] = part[blockDim.x - 1];
 }
 
+// wbase[w] = number of non-zero digits in windows < w; wbase[W] = total length of `sorted`
+__global__ void k_wbase(const uint32_t* __restrict__ base1, int ncoarse, int W, uint32_t* __restrict__ wbase,
+                        uint32_t* __restrict__ goff_end) {
+  if (blockIdx.x || threadIdx.x) return;
+  uint32_t run = 0;
+  for (int w = 0; w < W; w++) {
+    wbase[w] = run;
+    run += base1[(uint64_t)w * (ncoarse + 1) + ncoarse];
+  }
+  wbase[W] = run;
+  *goff_end = run;
+}
+
 __global__ void __launch_bounds__(512) k_scatter1(const uint32_t* __restrict__ dig, uint64_t M, int fbits, int ncoarse,
                                                   uint32_t tile, uint32_t ntiles, const uint32_t* __restrict__ hmat,
                                                   const uint32_t* __restrict__ base1, uint2* __restrict__ l1) {
@@ -162,6 +175,7 @@ __global__ void __launch_bounds__(512) k_scatter1(const uint32_t* __restrict__ d
   for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
     uint32_t e = __ldg(d + i);
     uint32_t b = e & 0x7fffffffu;
+    if (!b) continue;
     uint32_t pos = atomicAdd(&sh[b >> fbits], 1u);
     out[pos] = make_uint2(b, (e & 0x80000000u) | (uint32_t)i);
   }
@@ -171,6 +185,7 @@ __global__ void __launch_bounds__(512) k_scatter1(const uint32_t* __restrict__ d
 // level 2: one block per (coarse bin, window): counting sort by the low fbits of the bucket
 __global__ void __launch_bounds__(256) k_sort2(const uint2* __restrict__ l1, uint64_t M, int fbits, int ncoarse,
                                                uint32_t nb, int W, const uint32_t* __restrict__ base1,
+                                               const uint32_t* __restrict__ wbase_arr,
                                                uint32_t* __restrict__ sorted, uint32_t* __restrict__ goff) {
   extern __shared__ uint32_t sh[];   // [nfine] counters, then [256] scan scratch
   const int nfine = 1 << fbits;
@@ -200,7 +215,7 @@ __global__ void __launch_bounds__(256) k_sort2(const uint2* __restrict__ l1, uin
     __syncthreads();
   }
   uint32_t run = lo + (threadIdx.x ? scratch[threadIdx.x - 1] : 0);
-  uint64_t wbase = (uint64_t)w * M;   // positions are global over the concatenated windows
+  uint64_t wbase = wbase_arr[w];   // positions are global over the concatenated (compacted) windows
   for (int k = klo; k < khi; k++) {
     uint32_t v = cnt[k];
     cnt[k] = run;   // becomes the scatter cursor
@@ -208,7 +223,6 @@ __global__ void __launch_bounds__(256) k_sort2(const uint2* __restrict__ l1, uin
     if (b < nb) goff[(uint64_t)w * nb + b] = (uint32_t)(wbase + run);
     run += v;
   }
-  if (w == W - 1 && cb == ncoarse - 1 && threadIdx.x == 0) goff[(uint64_t)W * nb] = (uint32_t)((uint64_t)W * M);
   __syncthreads();
   uint32_t* out = sorted + wbase;
   for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
@@ -232,12 +246,13 @@ void launch_msm_sort(const MsmPlan& p, const MsmWorkspace& ws, const uint32_t* s
     int n = p.W * p.ncoarse;
     k_colscan1<<<(n + 255) / 256, 256, 0, st>>>(ws.hmat, p.ntiles, p.ncoarse, p.W, ws.tot);
     k_binscan1<<<p.W, 1024, 0, st>>>(ws.tot, p.ncoarse, ws.base1);
+    k_wbase<<<1, 32, 0, st>>>(ws.base1, p.ncoarse, p.W, ws.wbase, ws.goff + (size_t)p.W * p.nb);
   }
   k_scatter1<<<g1, 512, sh1, st>>>(ws.dig, M, p.fbits, p.ncoarse, p.tile, p.ntiles, ws.hmat, ws.base1, ws.l1);
   dim3 g2(p.ncoarse, p.W);
   size_t sh2 = ((size_t)(1u << p.fbits) + 256) * sizeof(uint32_t);
-  k_sort2<<<g2, 256, sh2, st>>>(ws.l1, M, p.fbits, p.ncoarse, p.nb, p.W, ws.base1, ws.sorted, ws.goff);
-  g_kernel_launches += 6;
+  k_sort2<<<g2, 256, sh2, st>>>(ws.l1, M, p.fbits, p.ncoarse, p.nb, p.W, ws.base1, ws.wbase, ws.sorted, ws.goff);
+  g_kernel_launches += 7;
 }
 
 }  // namespace bz

@@ -109,18 +109,21 @@ __global__ void k_ntt_tables(uint4* lo, uint4* hi, uint4* ninv, int log_root, in
 
 // ---------------------------------------------------------------------------------------------
 template <class F, int B>   // one in-place DIF round of radix 2^B on the shared tile
-__device__ __forceinline__ void dif_round(uint4* lo, uint4* hi, const uint4* trl, const uint4* trh, int R, int V,
-                                          int blk /*current block size*/, int tid, int nthreads) {
+__device__ __forceinline__ void dif_round(uint4* lo, uint4* hi, const uint4* trl, const uint4* trh, int lr,
+                                          int lblk /*log2 of the current block size*/, int tid, int nthreads) {
   typedef ff<F> A;
   typedef Fe<F> E;
   constexpr int RHO = 1 << B;
-  const int sub = blk / RHO;            // stride between the points of one butterfly group
+  constexpr int V = NTT_LANES;
+  const int R = 1 << lr;
+  const int lsub = lblk - B;
+  const int sub = 1 << lsub;            // stride between the points of one butterfly group
   const int items = V * (R / RHO);
-  const int tws = R / blk;              // w_blk = w_R^tws
+  const int tws = R >> lblk;            // w_blk = w_R^tws
   for (int w = tid; w < items; w += nthreads) {
     int v = w % V, grp = w / V;
-    int b0 = grp / sub, u = grp % sub;
-    int base = b0 * blk + u;
+    int b0 = grp >> lsub, u = grp & (sub - 1);
+    int base = (b0 << lblk) + u;
     E x[RHO];
 #pragma unroll
     for (int i = 0; i < RHO; i++) x[i] = nt<F>::lds(lo, hi, (base + i * sub) * V + v);
@@ -156,7 +159,7 @@ __device__ __forceinline__ void dif_round(uint4* lo, uint4* hi, const uint4* trl
 }
 
 template <class F>
-__global__ void __launch_bounds__(256, 1) k_ntt_pass(NttPassParams P) {
+__global__ void __launch_bounds__(256, 2) k_ntt_pass(NttPassParams P) {
   typedef ff<F> A;
   typedef Fe<F> E;
   extern __shared__ uint4 smem[];
@@ -175,11 +178,11 @@ __global__ void __launch_bounds__(256, 1) k_ntt_pass(NttPassParams P) {
   }
   // load (lane fastest: V adjacent work items are adjacent in memory), apply the pass twiddle
   for (int idx = tid; idx < R * V; idx += nth) {
-    int v = idx % V, r = idx / V;
+    int v = idx & (V - 1), r = idx / V;
     uint64_t q = qbase + v;
     if (q >= P.Q) continue;
-    uint64_t q0 = q % P.Q0, qr = q / P.Q0;
-    uint64_t q1 = qr % P.Q1, q2 = qr / P.Q1;
+    uint64_t q0 = q & (P.Q0 - 1), qr = q >> P.lq0;
+    uint64_t q1 = qr & (P.Q1 - 1), q2 = qr >> P.lq1;
     const uint4* src = P.in + 2 * (q0 * P.in_s0 + q1 * P.in_s1 + q2 * P.in_s2 + (uint64_t)r * P.in_sr);
     E x = nt<F>::ld(src);
     if (P.tw_sel >= 0 && r != 0) {
@@ -190,15 +193,15 @@ __global__ void __launch_bounds__(256, 1) k_ntt_pass(NttPassParams P) {
   }
   __syncthreads();
   // DIF rounds: radix 8 while possible, then 4 or 2
-  int blk = R, rem = P.lr;
-  while (rem >= 3) { dif_round<F, 3>(lo, hi, trl, trh, R, V, blk, tid, nth); blk >>= 3; rem -= 3; __syncthreads(); }
-  if (rem == 2) { dif_round<F, 2>(lo, hi, trl, trh, R, V, blk, tid, nth); __syncthreads(); }
-  if (rem == 1) { dif_round<F, 1>(lo, hi, trl, trh, R, V, blk, tid, nth); __syncthreads(); }
+  int lblk = P.lr, rem = P.lr;
+  while (rem >= 3) { dif_round<F, 3>(lo, hi, trl, trh, P.lr, lblk, tid, nth); lblk -= 3; rem -= 3; __syncthreads(); }
+  if (rem == 2) { dif_round<F, 2>(lo, hi, trl, trh, P.lr, lblk, tid, nth); __syncthreads(); }
+  if (rem == 1) { dif_round<F, 1>(lo, hi, trl, trh, P.lr, lblk, tid, nth); __syncthreads(); }
   // store: position p holds X[k], k = digit reversal of p over the round radices
   const int n8 = P.lr / 3, last = P.lr % 3;
   for (int idx = tid; idx < R * V; idx += nth) {
     int v, k;
-    if (P.store_k_fastest) { k = idx % R; v = idx / R; } else { v = idx % V; k = idx / V; }
+    if (P.store_k_fastest) { k = idx & (R - 1); v = idx >> P.lr; } else { v = idx % V; k = idx / V; }
     uint64_t q = qbase + v;
     if (q >= P.Q) continue;
     // p from k: k = m1 + 8 m2 + 64 m3 (+ ...), p = m1 R/8 + m2 R/64 + ...
@@ -206,19 +209,19 @@ __global__ void __launch_bounds__(256, 1) k_ntt_pass(NttPassParams P) {
     for (int t = 0; t < n8; t++) { sub >>= 3; p += (kk & 7) * sub; kk >>= 3; }
     if (last) { sub >>= last; p += (kk & ((1 << last) - 1)) * sub; }
     E x = nt<F>::lds(lo, hi, p * V + v);
-    uint64_t q0 = q % P.Q0, qr = q / P.Q0;
-    uint64_t q1 = qr % P.Q1, q2 = qr / P.Q1;
+    uint64_t q0 = q & (P.Q0 - 1), qr = q >> P.lq0;
+    uint64_t q1 = qr & (P.Q1 - 1), q2 = qr >> P.lq1;
     if (P.otw_sel >= 0) {
       uint64_t tq = P.otw_base + (P.otw_sel == 0 ? q0 : (P.otw_sel == 1 ? q1 : q2));
-      uint64_t e = ((uint64_t)k * tq) % ((uint64_t)1 << P.tab.log_root) * P.otw_scale;
+      uint64_t e = (((uint64_t)k * tq) & (((uint64_t)1 << P.tab.log_root) - 1)) * P.otw_scale;
       if (e) x = A::mul(x, nt<F>::tw(P.tab, e));
     }
     if (P.scale_ninv) x = A::mul(x, nt<F>::ld(P.tab.ninv));
     uint64_t off = q0 * P.out_s0 + q1 * P.out_s1 + q2 * P.out_s2;
     uint4* dst;
-    if (P.peer_rows) {
-      int h = k / P.peer_rows;
-      dst = P.peer_out[h] + 2 * (off + (uint64_t)(k % P.peer_rows) * P.out_sr);
+    if (P.peer_rows) {   // power of two
+      int h = k >> P.lpeer_rows;
+      dst = P.peer_out[h] + 2 * (off + (uint64_t)(k & (P.peer_rows - 1)) * P.out_sr);
     } else {
       dst = P.out + 2 * (off + (uint64_t)k * P.out_sr);
     }

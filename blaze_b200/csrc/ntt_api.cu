@@ -178,6 +178,8 @@ static int32_t ntt_enqueue(bz_ntt* t, int s) {
       P.store_k_fastest = 0;
     }
     P.scale_ninv = (t->inverse && p + 1 == t->radices.size()) ? 1 : 0;
+    P.lq0 = 0; while ((1ull << P.lq0) < P.Q0) P.lq0++;
+    P.lq1 = 0; while ((1ull << P.lq1) < P.Q1) P.lq1++;
     cudaError_t e = ntt_launch_pass(t->field, P, st);
     if (e != cudaSuccess) return bz_fail(BZ_ERR_UNKNOWN, "NTT pass launch failed: %s", cudaGetErrorString(e));
     t->cur[s] ^= 1;

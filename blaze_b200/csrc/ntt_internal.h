@@ -6,7 +6,7 @@
 
 namespace bz {
 
-#define NTT_LANES 8          // adjacent work items per CTA (8 x 32 B = 256-byte global runs)
+#define NTT_LANES 4          // adjacent work items per CTA (4 x 32 B = 128-byte global runs = one cache line)
 #define NTT_MAX_PEERS 8
 
 struct NttTables {
@@ -24,10 +24,12 @@ struct NttPassParams {
   const uint4* in;
   uint4* out;
   uint4* peer_out[NTT_MAX_PEERS];   // exchange pass: output row k lives on peer k / peer_rows
-  uint32_t peer_rows;               // 0 = not an exchange pass
+  uint32_t peer_rows;               // 0 = not an exchange pass; else a power of two
+  int lpeer_rows;
   int lr;                           // log2 of the pass radix R (1..9)
   uint64_t Q;
-  uint64_t Q0, Q1;
+  uint64_t Q0, Q1;                  // powers of two
+  int lq0, lq1;                     // their logs (index split by shift/mask, no 64-bit division)
   uint64_t in_s0, in_s1, in_s2, in_sr;
   uint64_t out_s0, out_s1, out_s2, out_sr;
   int tw_sel;                       // input twiddle w^(r * q[tw_sel] * tw_scale); -1 = none

@@ -92,6 +92,32 @@ def test_msm_edge_scalars(dclient, oracle):
         assert got == oracle.msm_naive("BLS12_381", bytes(pts), bytes(sc), n, 1)
 
 
+@pytest.mark.parametrize("kind", ["zeros_and_ones", "small_10bit", "all_equal", "sparse"])
+def test_msm_skewed_scalar_distributions(dclient, oracle, kind):
+    """Distributions real provers produce: mostly 0/1 witnesses, range-checked small values, one
+    repeated scalar (a single bucket per window holds everything), mostly-zero vectors.  Exercises
+    the zero-digit drop, the segment walk over huge buckets and the partial-merge tree."""
+    c = CURVE_BY_NAME["BLS12_381"]
+    n = 20000
+    pts, _, _ = chain_points(c, n, seed=77)
+    rng = np.random.default_rng(78)
+    if kind == "zeros_and_ones":
+        vals = rng.integers(0, 2, size=n).tolist()
+    elif kind == "small_10bit":
+        vals = rng.integers(0, 1024, size=n).tolist()
+    elif kind == "all_equal":
+        vals = [0x1d3c5b7a99f0e1d2c3b4a5968778695a4b3c2d1e0f] * n
+    else:
+        vals = [0] * n
+        for i in rng.integers(0, n, size=50):
+            vals[int(i)] = int.from_bytes(rng.bytes(31), "little")
+    sc = np.frombuffer(b"".join(int(v).to_bytes(32, "little") for v in vals), dtype=np.uint8).copy()
+    exp = oracle.msm_pippenger("BLS12_381", pts, sc, n)
+    for cb in (0, 9, 13):
+        got, _, plan = run_dma(dclient, Curve.BLS381, pts, sc, n, c=cb)
+        assert got == exp, (kind, plan)
+
+
 def test_msm_result_infinity(dclient):
     c = CURVE_BY_NAME["BLS12_381"]
     n = 4
