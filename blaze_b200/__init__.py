@@ -12,4 +12,7 @@ from .ingo_msm import (Curve, MSMClient, MSMImageParametrs, MSMInit, MSMInput, M
 
 from .ingo_ntt import NTT, NTTClient, NTTInput, NttInit          # noqa: F401
 
+from .ingo_hash import (Hash, PoseidonClient, PoseidonInitializeParameters, PoseidonResult, TreeMode,   # noqa: F401
+                        num_of_elements_in_base_layer, num_of_elements_oct_tree)
+
 __version__ = "0.1.0"

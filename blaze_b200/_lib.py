@@ -68,6 +68,18 @@ SIGNATURES = {
     "bz_ntt_result": [vp, sz, vp, sz],
     "bz_ntt_phase_times": [vp, ctypes.POINTER(ctypes.c_float), u32p],
     "bz_ntt_slot_device_ptr": [vp, sz, u64p],
+    "bz_poseidon_new": [vp, i32, ctypes.POINTER(vp)],
+    "bz_poseidon_free": [vp],
+    "bz_poseidon_loaded_binary_parameters": [vp, u32p],
+    "bz_poseidon_initialize": [vp, u32, i32, ctypes.c_char_p],
+    "bz_poseidon_set_data": [vp, vp, sz],
+    "bz_poseidon_start_process": [vp],
+    "bz_poseidon_wait_result": [vp],
+    "bz_poseidon_result": [vp, sz, vp, sz, ctypes.POINTER(sz)],
+    "bz_poseidon_get_last_element_sent_to_ring": [vp, u32p],
+    "bz_poseidon_get_num_of_pending_results": [vp, u32p],
+    "bz_poseidon_get_raw_results": [vp, u32, vp],
+    "bz_poseidon_get_last_hash_sent_to_host": [vp, u32p],
 }
 _RESTYPES = {"bz_last_error": ctypes.c_char_p, "bz_version": ctypes.c_char_p, "bz_kernel_launch_count": ctypes.c_uint64}
 

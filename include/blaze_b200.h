@@ -156,6 +156,31 @@ int32_t bz_ntt_phase_times(bz_ntt* t, float* total_ms, uint32_t* passes);
 /* device address of the buffer currently holding slot `buf_num` (device-resident use) */
 int32_t bz_ntt_slot_device_ptr(bz_ntt* t, size_t buf_num, uint64_t* dev_ptr);
 
+/* ------------------------------------------------------------------ PoseidonClient (src/ingo_hash/poseidon_api.rs)
+ * Stream of 32-byte little-endian BLS12-381 Fr elements in, 64-byte records out:
+ * hash[32] || meta[32], meta = LE(hash_id | layer_id << 30) (poseidon_api.rs:42-71).
+ * Tree: base node = Poseidon of 11 elements (TreeC) / 8 (TreeD), upper layers arity 8
+ * (ingo_hash/utils.rs:2-30); height h gives (8^h - 1)/7 records.  The reference's constants CSV is
+ * not in its repository: constants are generated by the library (see oracle/py/poseidon.py for the
+ * parameter set) -- hash VALUES are therefore not pinned to the FPGA image, counts and format are. */
+typedef enum bz_tree_mode { BZ_TREE_C = 0, BZ_TREE_D = 1 } bz_tree_mode;              /* utils.rs:16-30 */
+int32_t bz_poseidon_new(bz_dclient* dc, int32_t hash_type /* Hash::Poseidon = 0 */, bz_poseidon** out); /* :77-79 */
+int32_t bz_poseidon_free(bz_poseidon* p);
+int32_t bz_poseidon_loaded_binary_parameters(bz_poseidon* p, uint32_t out[2]);          /* :81-94   */
+/* PoseidonInitializeParameters{tree_height, tree_mode, instruction_path} (:19-24); a non-empty path must
+ * be readable (else BZ_ERR_LOAD_FAILED like :100-103) but its FPGA instruction words are not interpreted */
+int32_t bz_poseidon_initialize(bz_poseidon* p, uint32_t tree_height, int32_t tree_mode, const char* instruction_path); /* :96-111 */
+/* one element of <= 32 bytes (zero-extended), or a whole number of 32-byte elements */
+int32_t bz_poseidon_set_data(bz_poseidon* p, const uint8_t* input, size_t len);         /* :117-122 */
+int32_t bz_poseidon_start_process(bz_poseidon* p);                                       /* :113-115 (todo!() there) */
+int32_t bz_poseidon_wait_result(bz_poseidon* p);                                         /* :124-126 (todo!() there) */
+/* result(Some(expected)): drains records until `expected` were written to out (64 bytes each) */
+int32_t bz_poseidon_result(bz_poseidon* p, size_t expected, uint8_t* out, size_t out_cap_records, size_t* n_out); /* :128-146 */
+int32_t bz_poseidon_get_last_element_sent_to_ring(bz_poseidon* p, uint32_t* id);        /* :149-154 */
+int32_t bz_poseidon_get_num_of_pending_results(bz_poseidon* p, uint32_t* n);            /* :156-161 */
+int32_t bz_poseidon_get_raw_results(bz_poseidon* p, uint32_t num_of_results, uint8_t* out); /* :191-196 */
+int32_t bz_poseidon_get_last_hash_sent_to_host(bz_poseidon* p, uint32_t* id);           /* :198-203 */
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,129 @@
+"""Poseidon (x^5) over BLS12-381 Fr and the 8-ary Merkle tree builder of blaze's PoseidonClient.
+
+TEST INFRASTRUCTURE (oracle) -- see curves.py header.
+
+**PARITY UNPINNED.**  The reference streams its round constants / MDS / instruction words from a CSV
+that is not in the repository (/root/reference/src/ingo_hash/poseidon_api.rs:205-243) and its tests
+assert only the NUMBER of result records (tests/integration_poseidon.rs:101,165: 585 for height 4).
+What the reference does fix:
+  * field: TEST_SCALAR (integration_poseidon.rs:24-25) is < r(BLS12-381) and >= r(BLS12-377) => BLS12-381 Fr;
+  * tree shape: base-layer node = hash of 11 elements (integration_poseidon.rs:109-116), upper
+    layers arity 8 (ingo_hash/utils.rs:2-14) -- Filecoin "TreeC" (column hash + oct tree);
+  * record format: 64 bytes = hash[32] || meta[32], hash_id = LE32(meta[0..4]) & 0x3fffffff,
+    layer_id = LE32(meta[3..5] || 0 0) >> 6 (poseidon_api.rs:42-71), i.e. meta is the little-endian
+    integer hash_id | layer_id << 30.
+The parameter set chosen here (documented, generated in-repo, same on the CUDA side):
+  * S-box x^5, width t = arity + 1, R_F = 8 full rounds, R_P = 57 partial rounds for t = 9 and t = 12
+    (128-bit security table of the Poseidon paper for a 255-bit field);
+  * round constants: Grain LFSR stream of the Poseidon reference generator, initialised with
+    (field=1, sbox=0, n=255, t, R_F, R_P), rejection-sampled below r;
+  * MDS: Cauchy matrix M[i][j] = 1 / (x_i + y_j), x_i = i, y_j = t + j;
+  * sponge usage (Merkle-tree domain): state = [2^arity - 1, in_0 .. in_{arity-1}], output = state[1];
+  * round = add constants, S-box (all cells in full rounds, cell 0 in partial rounds), MDS.
+"""
+from .curves import BLS12_381
+
+R_ = BLS12_381.r
+R_F = 8
+R_P = {9: 57, 12: 57}
+TREE_C, TREE_D = 0, 1       # ingo_hash/utils.rs:16-30 (TreeMode::value)
+
+
+class Grain:
+    def __init__(self, n, t, r_f, r_p, field=1, sbox=0):
+        bits = []
+        for v, w in ((field, 2), (sbox, 4), (n, 12), (t, 12), (r_f, 10), (r_p, 10)):
+            bits += [int(b) for b in bin(v)[2:].zfill(w)]
+        bits += [1] * 30
+        assert len(bits) == 80
+        self.s = bits
+        for _ in range(160):
+            self._step()
+
+    def _step(self):
+        s = self.s
+        b = s[62] ^ s[51] ^ s[38] ^ s[23] ^ s[13] ^ s[0]
+        s.pop(0)
+        s.append(b)
+        return b
+
+    def bit(self):
+        # self-shrinking: take a pair; if the first bit is 1 output the second, else discard it
+        while True:
+            a = self._step()
+            b = self._step()
+            if a == 1:
+                return b
+
+    def field_element(self, n, p):
+        while True:
+            v = 0
+            for _ in range(n):
+                v = (v << 1) | self.bit()
+            if v < p:
+                return v
+
+
+_CACHE = {}
+
+
+def params(t):
+    """(round_constants[(R_F+R_P)*t], mds[t][t]) for width t."""
+    if t not in _CACHE:
+        g = Grain(255, t, R_F, R_P[t])
+        rc = [g.field_element(255, R_) for _ in range((R_F + R_P[t]) * t)]
+        mds = [[pow(i + (t + j), -1, R_) for j in range(t)] for i in range(t)]
+        _CACHE[t] = (rc, mds)
+    return _CACHE[t]
+
+
+def permute(state):
+    t = len(state)
+    rc, mds = params(t)
+    nr = R_F + R_P[t]
+    s = list(state)
+    for r in range(nr):
+        s = [(x + rc[r * t + i]) % R_ for i, x in enumerate(s)]
+        if r < R_F // 2 or r >= R_F // 2 + R_P[t]:
+            s = [pow(x, 5, R_) for x in s]
+        else:
+            s[0] = pow(s[0], 5, R_)
+        s = [sum(mds[i][j] * s[j] for j in range(t)) % R_ for i in range(t)]
+    return s
+
+
+def hash_elems(elems):
+    arity = len(elems)
+    return permute([(1 << arity) - 1] + [e % R_ for e in elems])[1]
+
+
+def tree_sizes(height):
+    """nodes per layer, base layer first (ingo_hash/utils.rs:2-14)."""
+    return [8 ** (height - 1 - l) for l in range(height)]
+
+
+def build_tree(elems, height, tree_mode=TREE_C):
+    """All node hashes, layer by layer (base layer first).  TreeC: 11 elements per base node;
+    TreeD: 8."""
+    in_arity = 11 if tree_mode == TREE_C else 8
+    sizes = tree_sizes(height)
+    assert len(elems) == in_arity * sizes[0]
+    layers = [[hash_elems(elems[i * in_arity:(i + 1) * in_arity]) for i in range(sizes[0])]]
+    for l in range(1, height):
+        prev = layers[-1]
+        layers.append([hash_elems(prev[i * 8:(i + 1) * 8]) for i in range(sizes[l])])
+    return layers
+
+
+def record(hash_val, hash_id, layer_id):
+    meta = (hash_id & 0x3fffffff) | (layer_id << 30)
+    return int(hash_val).to_bytes(32, "little") + meta.to_bytes(32, "little")
+
+
+def parse_record(rec):
+    """poseidon_api.rs:42-71"""
+    h = rec[:32]
+    meta = rec[32:]
+    hash_id = int.from_bytes(meta[0:4], "little") & 0x3fffffff
+    layer_id = int.from_bytes(meta[3:5] + b"\0\0", "little") >> 6
+    return h, hash_id, layer_id
