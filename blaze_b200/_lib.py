@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libblaze_b200.so")
+LIB_PATH = os.environ.get("BLAZE_B200_LIB") or os.path.join(_HERE, "libblaze_b200.so")   # override: A/B builds only
 _lib = None
 
 u8p = ctypes.POINTER(ctypes.c_uint8)

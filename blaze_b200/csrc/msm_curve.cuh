@@ -119,8 +119,11 @@ __global__ void __launch_bounds__(128) k_points_to_mont(const uint8_t* __restric
 
 // ---------------------------------------------------------------------------------------------
 // bucket accumulation (the dominant kernel)
+#ifndef BZ_ACC_MINBLOCKS
+#define BZ_ACC_MINBLOCKS 2
+#endif
 template <class C>
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(128, BZ_ACC_MINBLOCKS)
 k_accumulate(const AffineM<C>* __restrict__ table, const uint32_t* __restrict__ sorted,
              const uint32_t* __restrict__ goff, XyzzM<C>* __restrict__ buckets, uint32_t* __restrict__ part_id,
              XyzzM<C>* __restrict__ part_pt, uint64_t nseg, uint32_t L, uint32_t nb, uint32_t ngoff) {
