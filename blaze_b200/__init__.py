@@ -10,7 +10,7 @@ from .driver_client import CardType, DriverClient, DriverConfig, DriverPrimitive
 from .ingo_msm import (Curve, MSMClient, MSMImageParametrs, MSMInit, MSMInput, MSMParams, MSMResult,   # noqa: F401
                        PointMemoryType, PRECOMPUTE_FACTOR, PRECOMPUTE_FACTOR_BASE)
 
-from .ingo_ntt import NTT, NTTClient, NTTInput, NttInit          # noqa: F401
+from .ingo_ntt import NTT, DistributedNTT, NTTClient, NTTInput, NttInit          # noqa: F401
 
 from .ingo_hash import (Hash, PoseidonClient, PoseidonInitializeParameters, PoseidonResult, TreeMode,   # noqa: F401
                         num_of_elements_in_base_layer, num_of_elements_oct_tree)

@@ -68,6 +68,17 @@ SIGNATURES = {
     "bz_ntt_result": [vp, sz, vp, sz],
     "bz_ntt_phase_times": [vp, ctypes.POINTER(ctypes.c_float), u32p],
     "bz_ntt_slot_device_ptr": [vp, sz, u64p],
+    "bz_ntt_dist_new": [vp, i32, i32, i32, i32, i32, ctypes.POINTER(vp)],
+    "bz_ntt_dist_free": [vp],
+    "bz_ntt_dist_ipc_handle": [vp, vp],
+    "bz_ntt_dist_open_peers": [vp, vp],
+    "bz_ntt_dist_set_input": [vp, vp, sz],
+    "bz_ntt_dist_get_output": [vp, vp, sz],
+    "bz_ntt_dist_buffers": [vp, u64p, u64p, u64p],
+    "bz_ntt_dist_step1": [vp],
+    "bz_ntt_dist_sync": [vp],
+    "bz_ntt_dist_step3": [vp],
+    "bz_ntt_dist_times": [vp, ctypes.POINTER(ctypes.c_float)],
     "bz_poseidon_new": [vp, i32, ctypes.POINTER(vp)],
     "bz_poseidon_free": [vp],
     "bz_poseidon_loaded_binary_parameters": [vp, u32p],

@@ -211,9 +211,10 @@ __global__ void __launch_bounds__(256, 2) k_ntt_pass(NttPassParams P) {
     E x = nt<F>::lds(lo, hi, p * V + v);
     uint64_t q0 = q & (P.Q0 - 1), qr = q >> P.lq0;
     uint64_t q1 = qr & (P.Q1 - 1), q2 = qr >> P.lq1;
-    if (P.otw_sel >= 0) {
-      uint64_t tq = P.otw_base + (P.otw_sel == 0 ? q0 : (P.otw_sel == 1 ? q1 : q2));
-      uint64_t e = (((uint64_t)k * tq) & (((uint64_t)1 << P.tab.log_root) - 1)) * P.otw_scale;
+    if (P.otw_rsel >= 0) {
+      uint64_t row = (P.otw_rsel == 0 ? q0 : (P.otw_rsel == 1 ? q1 : q2)) * P.otw_ra + (uint64_t)k * P.otw_rb;
+      uint64_t col = P.otw_base + q0;
+      uint64_t e = ((row * col) & (((uint64_t)1 << P.tab.log_root) - 1)) * P.otw_scale;
       if (e) x = A::mul(x, nt<F>::tw(P.tab, e));
     }
     if (P.scale_ninv) x = A::mul(x, nt<F>::ld(P.tab.ninv));

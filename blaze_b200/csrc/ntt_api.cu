@@ -161,7 +161,7 @@ static int32_t ntt_enqueue(bz_ntt* t, int s) {
     P.lr = lr;
     P.Q = L / R;
     P.in_sr = L / R;
-    P.otw_sel = -1;
+    P.otw_rsel = -1;
     P.tab = t->tab;
     if (Ns == 1) {
       P.Q0 = P.Q; P.Q1 = 1;
@@ -249,5 +249,277 @@ extern "C" int32_t bz_ntt_slot_device_ptr(bz_ntt* t, size_t buf_num, uint64_t* d
   if (rc) return rc;
   CUDA_TRY(BZ_ERR_UNKNOWN, cudaStreamSynchronize(dc_stream(t->dc)));
   *dev_ptr = (uint64_t)(uintptr_t)t->buf[buf_num][t->cur[buf_num]];
+  return BZ_OK;
+}
+
+// =====================================================================================================
+// Multi-GPU four-step NTT (B200 addition).  One process per GPU; rank g of G.
+//   N = N1 x N2, input index j = j1 N2 + j2, output index k = k1 + N1 k2.
+//   rank g holds the column slab  A_g[j1][c] = in[j1 N2 + g C + c],  C = N2 / G        (N1 x C)
+//   step 1: length-N1 transforms down the columns (1-2 passes); the LAST pass multiplies by the
+//           four-step twiddle w^((g C + c) k1) and stores row k1 straight into the owner's exchange
+//           buffer B_h[k1 mod T][g C + c], h = k1 / T, T = N1 / G -- peer stores over NVLink: the
+//           all-to-all transpose is fused into the kernel epilogue, there is no separate collective.
+//   (host barrier between the steps: every rank must have finished writing every B)
+//   step 3: length-N2 transforms along the rows of B_h (1-2 passes); result O_h[k2][t] = X[(h T + t) + N1 k2].
+// In/out layouts are the strided slabs above (cudaMemcpy2D from / to a natural-order host vector).
+struct bz_ntt_dist {
+  bz_dclient* dc = nullptr;
+  int field = 2, log_n = 0, inverse = 0, rank = 0, world = 1;
+  int l1 = 0, l2 = 0;
+  uint64_t N1 = 0, N2 = 0, C = 0, T = 0, per = 0;   // per = N / G elements per rank
+  uint4 *A = nullptr, *B = nullptr, *I = nullptr, *O = nullptr;
+  uint4* peerB[NTT_MAX_PEERS] = {nullptr};
+  bool peers_open = false;
+  uint4* tab_mem = nullptr;
+  NttTables tab{};
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  float ms[2] = {0, 0};
+};
+
+static int ilog2u(uint64_t v) { int l = 0; while ((1ull << l) < v) l++; return l; }
+
+extern "C" int32_t bz_ntt_dist_new(bz_dclient* dc, int32_t field, int32_t log_size, int32_t inverse, int32_t rank,
+                                   int32_t world, bz_ntt_dist** out) {
+  if (!out) return bz_fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "out is null");
+  *out = nullptr;
+  int32_t rc = dc_select(dc);
+  if (rc) return rc;
+  if (field < 0 || field > 2) return bz_fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "unknown field %d", field);
+  if (world < 1 || world > NTT_MAX_PEERS || (world & (world - 1)) || rank < 0 || rank >= world)
+    return bz_fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "bad rank/world %d/%d (world must be a power of two <= %d)", rank, world, NTT_MAX_PEERS);
+  if (log_size > ntt_two_adicity(field) || log_size > 30) return bz_fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "log size %d unsupported", log_size);
+  int lw = ilog2u(world);
+  int l1 = log_size / 2, l2 = log_size - l1;
+  // the last column pass needs radix >= world, and each rank at least one row / column
+  if (l1 < lw || l2 < lw || l1 < 1) return bz_fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "2^%d is too small for %d ranks", log_size, world);
+  bz_ntt_dist* t = new bz_ntt_dist();
+  t->dc = dc; t->field = field; t->log_n = log_size; t->inverse = inverse ? 1 : 0; t->rank = rank; t->world = world;
+  t->l1 = l1; t->l2 = l2;
+  t->N1 = 1ull << l1; t->N2 = 1ull << l2; t->C = t->N2 / world; t->T = t->N1 / world;
+  t->per = (1ull << log_size) / world;
+  size_t bytes = t->per * 32;
+  cudaStream_t st = dc_stream(dc);
+  for (uint4** b : {&t->A, &t->B, &t->I, &t->O}) {
+    if (cudaMalloc((void**)b, bytes) != cudaSuccess) { bz_ntt_dist_free(t); return bz_fail(BZ_ERR_WRITE, "device allocation of %zu bytes failed", bytes); }
+    cudaMemsetAsync(*b, 0, bytes, st);
+  }
+  const int lo_bits = 14;
+  uint32_t nlo = 1u << std::min(log_size, lo_bits);
+  uint32_t nhi = log_size > lo_bits ? 1u << (log_size - lo_bits) : 1u;
+  if (cudaMalloc((void**)&t->tab_mem, ((size_t)nlo + nhi + 1) * 32) != cudaSuccess) { bz_ntt_dist_free(t); return bz_fail(BZ_ERR_WRITE, "table allocation failed"); }
+  t->tab.lo = t->tab_mem;
+  t->tab.hi = t->tab_mem + 2 * (size_t)nlo;
+  t->tab.ninv = t->tab_mem + 2 * ((size_t)nlo + nhi);
+  t->tab.lo_bits = lo_bits;
+  t->tab.log_root = log_size;
+  ntt_gen_tables(field, t->tab, log_size, t->inverse, st);
+  for (auto& e : t->ev) cudaEventCreate(&e);
+  if (world == 1) { t->peerB[0] = t->B; t->peers_open = true; }
+  CUDA_TRY(BZ_ERR_UNKNOWN, cudaStreamSynchronize(st));
+  *out = t;
+  return BZ_OK;
+}
+
+extern "C" int32_t bz_ntt_dist_free(bz_ntt_dist* t) {
+  if (!t) return BZ_OK;
+  cudaSetDevice(dc_device(t->dc));
+  cudaStreamSynchronize(dc_stream(t->dc));
+  if (t->world > 1 && t->peers_open)
+    for (int h = 0; h < t->world; h++) if (h != t->rank && t->peerB[h]) cudaIpcCloseMemHandle(t->peerB[h]);
+  for (uint4* b : {t->A, t->B, t->I, t->O, t->tab_mem}) if (b) cudaFree(b);
+  for (auto& e : t->ev) if (e) cudaEventDestroy(e);
+  delete t;
+  return BZ_OK;
+}
+
+extern "C" int32_t bz_ntt_dist_ipc_handle(bz_ntt_dist* t, uint8_t out[64]) {
+  if (!t || !out) return bz_fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null argument");
+  int32_t rc = dc_select(t->dc);
+  if (rc) return rc;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  CUDA_TRY(BZ_ERR_UNKNOWN, cudaIpcGetMemHandle(&h, t->B));
+  memcpy(out, &h, 64);
+  return BZ_OK;
+}
+
+extern "C" int32_t bz_ntt_dist_open_peers(bz_ntt_dist* t, const uint8_t* handles /* world x 64 bytes, rank order */) {
+  if (!t || !handles) return bz_fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null argument");
+  int32_t rc = dc_select(t->dc);
+  if (rc) return rc;
+  for (int h = 0; h < t->world; h++) {
+    if (h == t->rank) { t->peerB[h] = t->B; continue; }
+    cudaIpcMemHandle_t mh;
+    memcpy(&mh, handles + (size_t)h * 64, 64);
+    void* p = nullptr;
+    CUDA_TRY(BZ_ERR_UNKNOWN, cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
+    t->peerB[h] = (uint4*)p;
+  }
+  t->peers_open = true;
+  return BZ_OK;
+}
+
+// host natural-order vector -> this rank's column slab A (strided copy)
+extern "C" int32_t bz_ntt_dist_set_input(bz_ntt_dist* t, const uint8_t* full_input, size_t len) {
+  if (!t || !full_input) return bz_fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null argument");
+  if (len != ((size_t)32 << t->log_n)) return bz_fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "input must be the full 2^%d x 32 B vector", t->log_n);
+  int32_t rc = dc_select(t->dc);
+  if (rc) return rc;
+  cudaStream_t st = dc_stream(t->dc);
+  CUDA_TRY(BZ_ERR_WRITE, cudaMemcpy2DAsync(t->A, t->C * 32, full_input + (size_t)t->rank * t->C * 32, t->N2 * 32, t->C * 32, t->N1,
+                                           cudaMemcpyHostToDevice, st));
+  CUDA_TRY(BZ_ERR_WRITE, cudaStreamSynchronize(st));
+  return BZ_OK;
+}
+
+// this rank's output block O[k2][t] -> natural-order host vector positions (rank T + t) + N1 k2
+extern "C" int32_t bz_ntt_dist_get_output(bz_ntt_dist* t, uint8_t* full_output, size_t len) {
+  if (!t || !full_output) return bz_fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null argument");
+  if (len != ((size_t)32 << t->log_n)) return bz_fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "output must be the full 2^%d x 32 B vector", t->log_n);
+  int32_t rc = dc_select(t->dc);
+  if (rc) return rc;
+  cudaStream_t st = dc_stream(t->dc);
+  CUDA_TRY(BZ_ERR_READ, cudaMemcpy2DAsync(full_output + (size_t)t->rank * t->T * 32, t->N1 * 32, t->O, t->T * 32, t->T * 32, t->N2,
+                                          cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(BZ_ERR_READ, cudaStreamSynchronize(st));
+  return BZ_OK;
+}
+
+extern "C" int32_t bz_ntt_dist_buffers(bz_ntt_dist* t, uint64_t* slab_in_dev, uint64_t* block_out_dev, uint64_t* elems_per_rank) {
+  if (!t) return bz_fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null argument");
+  if (slab_in_dev) *slab_in_dev = (uint64_t)(uintptr_t)t->A;
+  if (block_out_dev) *block_out_dev = (uint64_t)(uintptr_t)t->O;
+  if (elems_per_rank) *elems_per_rank = t->per;
+  return BZ_OK;
+}
+
+static void fill_logs(NttPassParams& P) {
+  P.lq0 = ilog2u(P.Q0);
+  P.lq1 = ilog2u(P.Q1);
+  P.lpeer_rows = P.peer_rows ? ilog2u(P.peer_rows) : 0;
+}
+
+extern "C" int32_t bz_ntt_dist_step1(bz_ntt_dist* t) {
+  if (!t) return bz_fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null argument");
+  if (!t->peers_open) return bz_fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "open_peers has not been called");
+  int32_t rc = dc_select(t->dc);
+  if (rc) return rc;
+  cudaStream_t st = dc_stream(t->dc);
+  const uint64_t N = 1ull << t->log_n, N1 = t->N1, N2 = t->N2, C = t->C;
+  std::vector<int> rad = plan_radices(t->l1);
+  if (rad.empty()) rad.push_back(0);
+  cudaEventRecord(t->ev[0], st);
+  const uint4* cur = t->A;
+  uint64_t Ns = 1;
+  for (size_t p = 0; p < rad.size(); p++) {
+    int lr = rad[p];
+    uint64_t R = 1ull << lr;
+    bool last = p + 1 == rad.size();
+    NttPassParams P;
+    memset(&P, 0, sizeof(P));
+    P.tab = t->tab;
+    P.lr = lr;
+    P.in = cur;
+    P.Q = (N1 / R) * C;
+    P.Q0 = C;
+    P.in_s0 = 1; P.out_s0 = 1;
+    P.tw_sel = -1;
+    P.otw_rsel = -1;
+    if (Ns == 1) {
+      P.Q1 = 1;
+      P.in_s2 = C; P.in_sr = (N1 / R) * C;
+      P.out_s2 = R * C; P.out_sr = C;
+    } else {
+      P.Q1 = Ns;
+      P.in_s1 = C; P.in_s2 = Ns * C; P.in_sr = (N1 / R) * C;
+      P.out_s1 = C; P.out_s2 = Ns * R * C; P.out_sr = Ns * C;
+      P.tw_sel = 1;
+      P.tw_scale = N / (Ns * R);
+    }
+    if (last) {
+      if (R < (uint64_t)t->world) return bz_fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "last column radix %llu < world %d", (unsigned long long)R, t->world);
+      P.otw_rsel = 1; P.otw_ra = 1; P.otw_rb = Ns; P.otw_base = (uint64_t)t->rank * C; P.otw_scale = 1;
+      P.peer_rows = (uint32_t)(R / t->world);
+      P.out_s0 = 1; P.out_s1 = N2; P.out_s2 = 0; P.out_sr = Ns * N2;
+      for (int h = 0; h < t->world; h++) P.peer_out[h] = t->peerB[h] + 2 * ((uint64_t)t->rank * C);
+      P.out = nullptr;
+    } else {
+      P.out = (cur == t->A) ? t->I : const_cast<uint4*>(t->A);
+    }
+    fill_logs(P);
+    cudaError_t e = ntt_launch_pass(t->field, P, st);
+    if (e != cudaSuccess) return bz_fail(BZ_ERR_UNKNOWN, "NTT column pass failed: %s", cudaGetErrorString(e));
+    cur = P.out;
+    Ns *= R;
+  }
+  cudaEventRecord(t->ev[1], st);
+  return BZ_OK;
+}
+
+extern "C" int32_t bz_ntt_dist_sync(bz_ntt_dist* t) {
+  if (!t) return bz_fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null argument");
+  int32_t rc = dc_select(t->dc);
+  if (rc) return rc;
+  CUDA_TRY(BZ_ERR_UNKNOWN, cudaStreamSynchronize(dc_stream(t->dc)));
+  return BZ_OK;
+}
+
+extern "C" int32_t bz_ntt_dist_step3(bz_ntt_dist* t) {
+  if (!t) return bz_fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null argument");
+  int32_t rc = dc_select(t->dc);
+  if (rc) return rc;
+  cudaStream_t st = dc_stream(t->dc);
+  const uint64_t N = 1ull << t->log_n, N2 = t->N2, T = t->T;
+  std::vector<int> rad = plan_radices(t->l2);
+  cudaEventRecord(t->ev[2], st);
+  const uint4* cur = t->B;
+  uint64_t Ns = 1;
+  for (size_t p = 0; p < rad.size(); p++) {
+    int lr = rad[p];
+    uint64_t R = 1ull << lr;
+    bool last = p + 1 == rad.size();
+    NttPassParams P;
+    memset(&P, 0, sizeof(P));
+    P.tab = t->tab;
+    P.lr = lr;
+    P.in = cur;
+    P.tw_sel = -1;
+    P.otw_rsel = -1;
+    P.Q = (N2 / R) * T;
+    if (p == 0 && !last) {          // rows in (contiguous), transposed out: I[pos][t]
+      P.Q0 = N2 / R; P.Q1 = T;
+      P.in_s0 = 1; P.in_s1 = N2; P.in_sr = N2 / R;
+      P.out_s0 = R * T; P.out_s1 = 1; P.out_sr = T;
+    } else if (p == 0 && last) {    // single pass: rows in, O[k2][t] out
+      P.Q0 = T; P.Q1 = 1;
+      P.in_s0 = N2; P.in_sr = 1;
+      P.out_s0 = 1; P.out_sr = T;
+    } else {                        // lanes along t on I[pos][t]
+      P.Q0 = T; P.Q1 = Ns;
+      P.in_s0 = 1; P.in_s1 = T; P.in_s2 = Ns * T; P.in_sr = (N2 / R) * T;
+      P.out_s0 = 1; P.out_s1 = T; P.out_s2 = Ns * R * T; P.out_sr = Ns * T;
+      P.tw_sel = 1;
+      P.tw_scale = N / (Ns * R);
+    }
+    P.out = last ? t->O : ((cur == t->I) ? t->A : t->I);
+    P.scale_ninv = (t->inverse && last) ? 1 : 0;
+    fill_logs(P);
+    cudaError_t e = ntt_launch_pass(t->field, P, st);
+    if (e != cudaSuccess) return bz_fail(BZ_ERR_UNKNOWN, "NTT row pass failed: %s", cudaGetErrorString(e));
+    cur = P.out;
+    Ns *= R;
+  }
+  cudaEventRecord(t->ev[3], st);
+  return BZ_OK;
+}
+
+extern "C" int32_t bz_ntt_dist_times(bz_ntt_dist* t, float ms[2]) {
+  if (!t || !ms) return bz_fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null argument");
+  int32_t rc = dc_select(t->dc);
+  if (rc) return rc;
+  CUDA_TRY(BZ_ERR_UNKNOWN, cudaStreamSynchronize(dc_stream(t->dc)));
+  cudaEventElapsedTime(&ms[0], t->ev[0], t->ev[1]);
+  cudaEventElapsedTime(&ms[1], t->ev[2], t->ev[3]);
   return BZ_OK;
 }

@@ -23,7 +23,9 @@ struct NttTables {
 struct NttPassParams {
   const uint4* in;
   uint4* out;
-  uint4* peer_out[NTT_MAX_PEERS];   // exchange pass: output row k lives on peer k / peer_rows
+  // exchange pass (last column pass of a multi-GPU four-step): output k of a work item goes to peer
+  // k / peer_rows at peer_out[peer] + item offset + (k % peer_rows) * out_sr; stores travel over NVLink
+  uint4* peer_out[NTT_MAX_PEERS];
   uint32_t peer_rows;               // 0 = not an exchange pass; else a power of two
   int lpeer_rows;
   int lr;                           // log2 of the pass radix R (1..9)
@@ -34,8 +36,10 @@ struct NttPassParams {
   uint64_t out_s0, out_s1, out_s2, out_sr;
   int tw_sel;                       // input twiddle w^(r * q[tw_sel] * tw_scale); -1 = none
   uint64_t tw_scale;
-  int otw_sel;                      // output twiddle w^(k * (otw_base + q[otw_sel]) * otw_scale); -1 = none
-  uint64_t otw_base, otw_scale;
+  // output twiddle w^((row * col mod 2^log_root) * otw_scale), row = q[otw_rsel] * otw_ra + k * otw_rb,
+  // col = otw_base + q0 (the four-step twiddle between the column and the row transforms); otw_rsel < 0 = none
+  int otw_rsel;
+  uint64_t otw_ra, otw_rb, otw_base, otw_scale;
   int store_k_fastest;              // store loop order (k fastest when a work item's outputs are contiguous)
   int scale_ninv;                   // multiply outputs by (2^log_root)^-1 (last pass of an inverse transform)
   NttTables tab;

@@ -104,3 +104,70 @@ class NTTClient(DriverPrimitive):
         v = ctypes.c_uint64()
         check(lib().bz_ntt_slot_device_ptr(self._h, int(buf_num), ctypes.byref(v)))
         return v.value
+
+
+class DistributedNTT:
+    """Multi-GPU four-step NTT, one instance per rank (B200 addition, include/blaze_b200.h `bz_ntt_dist_*`).
+
+    `exchange(handle_bytes) -> list of all ranks' handle bytes` is supplied by the caller (e.g.
+    torch.distributed.all_gather_object); `barrier()` likewise.  With world == 1 both may be None."""
+
+    def __init__(self, dclient: DriverClient, log_size, rank=0, world=1, field=2, inverse=False, exchange=None,
+                 barrier=None):
+        self.dclient = dclient
+        self.rank, self.world, self.log_size = rank, world, log_size
+        self.nbytes = (1 << log_size) * 32
+        self._barrier = barrier or (lambda: None)
+        h = ctypes.c_void_p()
+        check(lib().bz_ntt_dist_new(dclient._h, int(field), int(log_size), 1 if inverse else 0, rank, world,
+                                    ctypes.byref(h)))
+        self._h = h
+        if world > 1:
+            mine = ctypes.create_string_buffer(64)
+            check(lib().bz_ntt_dist_ipc_handle(self._h, mine))
+            handles = exchange(mine.raw)
+            assert len(handles) == world
+            blob = b"".join(handles)
+            check(lib().bz_ntt_dist_open_peers(self._h, ctypes.c_char_p(blob)))
+        self._barrier()
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._barrier()
+            lib().bz_ntt_dist_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                lib().bz_ntt_dist_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def set_input(self, full_input):
+        p, n, keep = buf_ptr(full_input)
+        check(lib().bz_ntt_dist_set_input(self._h, p, n))
+
+    def get_output(self, full_output):
+        p, n, keep = buf_ptr(full_output)
+        check(lib().bz_ntt_dist_get_output(self._h, p, n))
+
+    def run(self):
+        """step1 (columns + twiddle + peer stores) -> barrier -> step3 (rows)."""
+        self._barrier()                 # every rank's exchange buffer is free again
+        check(lib().bz_ntt_dist_step1(self._h))
+        check(lib().bz_ntt_dist_sync(self._h))
+        self._barrier()                 # every rank has finished writing every exchange buffer
+        check(lib().bz_ntt_dist_step3(self._h))
+        check(lib().bz_ntt_dist_sync(self._h))
+
+    def times(self):
+        out = (ctypes.c_float * 2)()
+        check(lib().bz_ntt_dist_times(self._h, out))
+        return {"step1_ms": out[0], "step3_ms": out[1]}
+
+    def buffers(self):
+        a, o, n = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+        check(lib().bz_ntt_dist_buffers(self._h, ctypes.byref(a), ctypes.byref(o), ctypes.byref(n)))
+        return a.value, o.value, n.value

@@ -156,6 +156,26 @@ int32_t bz_ntt_phase_times(bz_ntt* t, float* total_ms, uint32_t* passes);
 /* device address of the buffer currently holding slot `buf_num` (device-resident use) */
 int32_t bz_ntt_slot_device_ptr(bz_ntt* t, size_t buf_num, uint64_t* dev_ptr);
 
+/* Multi-GPU four-step NTT, one process per GPU (B200 addition; config 4 of BASELINE.json).  N = N1 x N2:
+ * rank g of G holds the column slab in[j1 N2 + g C + c] (C = N2/G); step1 transforms the columns and
+ * its last pass stores every output row, already multiplied by the four-step twiddle, straight into
+ * the owning rank's exchange buffer (peer stores over NVLink -- the transpose is fused into the kernel);
+ * after a host barrier step3 transforms the rows; rank h ends with X[(h T + t) + N1 k2] (T = N1/G).
+ * Exchange buffers are shared through CUDA IPC handles (64 bytes each) passed around by the caller. */
+typedef struct bz_ntt_dist bz_ntt_dist;
+int32_t bz_ntt_dist_new(bz_dclient* dc, int32_t field, int32_t log_size, int32_t inverse, int32_t rank, int32_t world,
+                        bz_ntt_dist** out);
+int32_t bz_ntt_dist_free(bz_ntt_dist* t);
+int32_t bz_ntt_dist_ipc_handle(bz_ntt_dist* t, uint8_t out[64]);
+int32_t bz_ntt_dist_open_peers(bz_ntt_dist* t, const uint8_t* handles /* world x 64 bytes in rank order */);
+int32_t bz_ntt_dist_set_input(bz_ntt_dist* t, const uint8_t* full_input, size_t len);    /* natural-order host vector in */
+int32_t bz_ntt_dist_get_output(bz_ntt_dist* t, uint8_t* full_output, size_t len);        /* fills this rank's part */
+int32_t bz_ntt_dist_buffers(bz_ntt_dist* t, uint64_t* slab_in_dev, uint64_t* block_out_dev, uint64_t* elems_per_rank);
+int32_t bz_ntt_dist_step1(bz_ntt_dist* t);
+int32_t bz_ntt_dist_sync(bz_ntt_dist* t);   /* drains the rank's stream; the cross-rank barrier is the caller's */
+int32_t bz_ntt_dist_step3(bz_ntt_dist* t);
+int32_t bz_ntt_dist_times(bz_ntt_dist* t, float ms[2]);   /* CUDA-event ms of the last step1 / step3 */
+
 /* ------------------------------------------------------------------ PoseidonClient (src/ingo_hash/poseidon_api.rs)
  * Stream of 32-byte little-endian BLS12-381 Fr elements in, 64-byte records out:
  * hash[32] || meta[32], meta = LE(hash_id | layer_id << 30) (poseidon_api.rs:42-71).
