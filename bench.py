@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--cpu-sample-log-n", type=int, default=18)
     ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ntt", action="store_true", help="skip the secondary metric (2^27 NTT ms)")
+    ap.add_argument("--ntt-log-n", type=int, default=27)
     return ap.parse_args()
 
 
@@ -118,6 +120,76 @@ def cpu_port_rate(log_n, threads=0, seed=900):
     capi.msm_pippenger("BLS12_381", pts, sc, n, th)
     dt = time.perf_counter() - t
     return n / dt, th, dt
+
+
+class _DevView:
+    """torch view of raw device memory owned by the library (via __cuda_array_interface__)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def ntt_section(args, bz, torch, dist, dc, rank, world, local):
+    """Secondary metric of BASELINE.json: 2^27 NTT over BLS12-381 Fr, ms (device-resident data).
+    N = 1: NTTClient (3 Stockham passes).  N > 1: four-step across the ranks, exchange fused into the
+    last column pass (peer stores over NVLink), one host barrier between the two steps."""
+    log_n = args.ntt_log_n
+    n = 1 << log_n
+    reps = max(3, args.steps)
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(1234 + rank)
+    if world == 1:
+        t = bz.NTTClient.new_ex(dc, 2, log_n, False)
+        t.initialize()
+        view = torch.as_tensor(_DevView(t.slot_device_ptr(0), n * 32), device="cuda")
+        view.copy_(torch.randint(0, 256, (n * 32,), dtype=torch.uint8, device="cuda", generator=gen))
+        view.view(n, 32)[:, 31] &= 0x3f          # canonical elements (< 2^254 < r)
+        torch.cuda.synchronize()
+        ms = []
+        for i in range(reps + 2):
+            t.start_process(0)
+            t.wait_result()
+            if i >= 2:
+                ms.append(t.phase_times()["total"])
+        passes = t.phase_times()["passes"]
+        t.close()
+        ms_val = sum(ms) / len(ms)
+        layout = "natural order in / natural order out, in place in slot 0"
+    else:
+        def exchange(h):
+            out = [None] * world
+            dist.all_gather_object(out, h)
+            return out
+        t = bz.DistributedNTT(dc, log_n, rank, world, exchange=exchange, barrier=dist.barrier)
+        a_ptr, o_ptr, per = t.buffers()
+        view = torch.as_tensor(_DevView(a_ptr, per * 32), device="cuda")
+        view.copy_(torch.randint(0, 256, (per * 32,), dtype=torch.uint8, device="cuda", generator=gen))
+        view.view(per, 32)[:, 31] &= 0x3f
+        torch.cuda.synchronize()
+        walls = []
+        for i in range(reps + 2):
+            dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            t.run()
+            dist.barrier()
+            if i >= 2:
+                walls.append(time.perf_counter() - t0)
+        tm = t.times()
+        v = torch.tensor([sum(walls) / len(walls), tm["step1_ms"], tm["step3_ms"]], dtype=torch.float64, device="cuda")
+        dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        ms_val = float(v[0]) * 1e3
+        passes = None
+        layout = ("rank g holds column slab in[j1*N2 + g*C + c] in, X[(h*T+t) + N1*k2] out (strided slabs); "
+                  "step1 %.2f ms + step3 %.2f ms device time, rest = 2 host barriers" % (float(v[1]), float(v[2])))
+        t.close()
+    hbm_peak, _ = peaks()
+    npass = passes if passes else 4
+    gbs = npass * 2 * n * 32 / world / (ms_val / 1e3) / 1e9
+    return {"metric": "2^%d NTT over BLS12-381 Fr, ms" % log_n, "ms": ms_val, "n_gpus": world, "passes": npass,
+            "layout": layout, "semantics": "arkworks Radix2EvaluationDomain::fft (natural in/out), forward",
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s per GPU", "frac": gbs / hbm_peak,
+                         "algorithmic_bytes": npass * 2 * n * 32}}
 
 
 def run_reference(args, rank, world):
@@ -282,6 +354,14 @@ def main():
     value = N / (ms_per_step / 1e3)
     e2e_value = N / (wall_e2e / args.steps)
 
+    ntt = None
+    if not args.no_ntt:
+        m_plan = m.plan_info()
+        try:
+            ntt = ntt_section(args, bz, torch, dist, dc, rank, world, local)
+        except Exception as e:     # the headline line must still be printed
+            ntt = {"error": repr(e)}
+
     if rank == 0:
         plan = m.plan_info()
         W, cbits = plan["windows"], plan["c"]
@@ -324,6 +404,8 @@ def main():
                                  "(IMAD.WIDE.U32, 4 issue cycles each) ~74% busy and DRAM ~5% "
                                  "(profiles/r1_ncu_k_accumulate_*.txt)"},
         }
+        if ntt is not None:
+            line["ntt"] = ntt
         if world == 1 and not args.no_cpu_baseline:
             from oracle import capi
             capi.build()

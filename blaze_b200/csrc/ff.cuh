@@ -156,7 +156,96 @@ struct ff {
     final_sub(r.v);
     return r;
   }
-  BZ_HDI static E sqr(const E& a) { return mul(a, a); }
+  // ---- dedicated squaring: N(N+1)/2 instead of N^2 partial products in the multiplication half.
+  // Row i adds a_i * V_i with V_i = a_i 2^(32 i) + 2 * (limbs above i of a) 2^(32(i+1)) -- the diagonal
+  // term once and every off-diagonal product doubled, so rows need no products below column i.  The
+  // doubled tail comes from d = a << 1 (limbwise funnel shift); its lowest limb drops the bit that
+  // would have carried in from a_i.  Doubling front-loads the partial sums: before the division of step
+  // i the accumulator is < 2^(32N) + 3 * 2^32 p, which fits the N+1-limb window only if p < 2^(32N-2).
+  // That holds for the three base fields and for Fr(BN254) / Fr(BLS12-377); Fr(BLS12-381) (255 bits in
+  // 256) keeps the generic product.
+  BZ_HDI static uint32_t sq_limb(const uint32_t* a, const uint32_t* d, int i, int j) {
+    return j == i ? a[i] : (j == i + 1 ? (d[j] & 0xfffffffeu) : d[j]);
+  }
+  template <int I>
+  BZ_HDI static void step_sqr(uint64_t* Ev, uint64_t* Ov, const uint32_t* a, const uint32_t* d) {
+    static_assert(F::BITS + 2 <= 32 * N, "front-loaded doubling needs two spare bits");
+    constexpr int NW = N / 2;
+    const uint32_t bi = a[I];
+    if (I == 0) {
+#pragma unroll
+      for (int k = 0; k < NW; k++) {
+        Ov[k] = cc::mul_wide(sq_limb(a, d, 0, 2 * k + 1), bi);
+        Ev[k] = cc::mul_wide(sq_limb(a, d, 0, 2 * k), bi);
+      }
+    } else {
+      uint64_t h = Ov[0] >> 32;
+      constexpr int K0 = I / 2;          // first odd-position product of this row: column 2 K0 + 1 >= I
+      constexpr int KE = (I + 1) / 2;    // first even-position product: column 2 KE >= I
+#pragma unroll
+      for (int k = 0; k < K0 && k < NW - 1; k++) Ov[k] = Ov[k + 1];
+      if (K0 < NW - 1) {
+        Ov[K0] = cc::add_cc64(Ov[K0 + 1], cc::mul_wide(sq_limb(a, d, I, 2 * K0 + 1), bi));
+#pragma unroll
+        for (int k = K0 + 1; k < NW - 1; k++)
+          Ov[k] = cc::addc_cc64(Ov[k + 1], cc::mul_wide(sq_limb(a, d, I, 2 * k + 1), bi));
+        Ov[NW - 1] = cc::addc64(0ull, cc::mul_wide(sq_limb(a, d, I, N - 1), bi));
+      } else {
+        Ov[NW - 1] = cc::mul_wide(sq_limb(a, d, I, N - 1), bi);
+      }
+      Ev[0] = cc::add_cc64(Ev[0], h);
+#pragma unroll
+      for (int k = 1; k < NW; k++)
+        Ev[k] = cc::addc_cc64(Ev[k], k >= KE ? cc::mul_wide(sq_limb(a, d, I, 2 * k), bi) : 0ull);
+      uint64_t c = cc::addc64(0ull, 0ull);
+      Ov[NW - 1] += c << 32;
+    }
+    uint32_t m = (uint32_t)Ev[0] * F::INV;
+    Ov[0] = cc::add_cc64(Ov[0], cc::mul_wide(F::mod()[1], m));
+#pragma unroll
+    for (int k = 1; k < NW - 1; k++) Ov[k] = cc::addc_cc64(Ov[k], cc::mul_wide(F::mod()[2 * k + 1], m));
+    Ov[NW - 1] = cc::addc64(Ov[NW - 1], cc::mul_wide(F::mod()[N - 1], m));
+    Ev[0] = cc::add_cc64(Ev[0], cc::mul_wide(F::mod()[0], m));
+#pragma unroll
+    for (int k = 1; k < NW; k++) Ev[k] = cc::addc_cc64(Ev[k], cc::mul_wide(F::mod()[2 * k], m));
+    uint64_t c2 = cc::addc64(0ull, 0ull);
+    Ov[NW - 1] += c2 << 32;
+  }
+  template <int I>
+  BZ_HDI static void sqr_rows(uint64_t* Ev, uint64_t* Ov, const uint32_t* a, const uint32_t* d) {
+    if constexpr (I < N) {
+      step_sqr<I>(Ev, Ov, a, d);
+      step_sqr<I + 1>(Ov, Ev, a, d);
+      sqr_rows<I + 2>(Ev, Ov, a, d);
+    }
+  }
+  BZ_HDI static E sqr(const E& a) {
+    if constexpr (F::BITS + 2 > 32 * N) {
+      return mul(a, a);
+    } else {
+      return sqr_dedicated(a);
+    }
+  }
+  BZ_HDI static E sqr_dedicated(const E& a) {
+    constexpr int NW = N / 2;
+    uint64_t Ev[NW], Ov[NW];
+    uint32_t d[N];
+    d[0] = a.v[0] << 1;
+#pragma unroll
+    for (int j = 1; j < N; j++) d[j] = (a.v[j] << 1) | (a.v[j - 1] >> 31);
+    sqr_rows<0>(Ev, Ov, a.v, d);
+    E r;
+    r.v[0] = cc::add_cc((uint32_t)Ev[0], (uint32_t)(Ov[0] >> 32));
+#pragma unroll
+    for (int j = 1; j < N - 1; j++) {
+      uint32_t e = (j & 1) ? (uint32_t)(Ev[j / 2] >> 32) : (uint32_t)Ev[j / 2];
+      uint32_t o = ((j + 1) & 1) ? (uint32_t)(Ov[(j + 1) / 2] >> 32) : (uint32_t)Ov[(j + 1) / 2];
+      r.v[j] = cc::addc_cc(e, o);
+    }
+    r.v[N - 1] = cc::addc((uint32_t)(Ev[NW - 1] >> 32), 0u);
+    final_sub(r.v);
+    return r;
+  }
 
   BZ_HDI static E to_mont(const E& a) {
     E r2;
