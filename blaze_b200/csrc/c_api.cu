@@ -289,8 +289,15 @@ struct bz_msm {
   bool table_from_arena = false;
   uint8_t* dma_points = nullptr;
   size_t dma_points_cap = 0;
-  uint32_t* scalars_dev = nullptr;
-  size_t scalars_cap = 0;
+  // scalar ingest: two staging buffers filled on a dedicated copy stream, so the H2D of task k+1
+  // overlaps the kernels of task k (the reference's task queue allows exactly that pipelining)
+  uint32_t* scalars_dev[2] = {nullptr, nullptr};
+  size_t scalars_cap[2] = {0, 0};
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr};     // copy stream: staging buffer b is filled
+  cudaEvent_t ev_consumed[2] = {nullptr, nullptr};   // work stream: k_digits has read staging buffer b
+  bool consumed_valid[2] = {false, false};
+  int stage_next = 0, stage_cur = -1;
   const uint32_t* scalars_src = nullptr;   // where the pending task reads its scalars from
   uint8_t* pinned = nullptr;   // RESULT_SLOTS result slots
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // start, sorted, acc begin, acc end, done
@@ -443,6 +450,11 @@ extern "C" int32_t bz_msm_new(bz_dclient* dc, int32_t curve, int32_t mem_type, i
   m->mem_type = mem_type;
   m->factor = is_precompute ? 8 : 1;   // PRECOMPUTE_FACTOR / PRECOMPUTE_FACTOR_BASE, msm_api.rs:39-40
   for (auto& e : m->ev) cudaEventCreate(&e);
+  cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking);
+  for (int b = 0; b < 2; b++) {
+    cudaEventCreateWithFlags(&m->ev_copied[b], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&m->ev_consumed[b], cudaEventDisableTiming);
+  }
   if (cudaHostAlloc((void**)&m->pinned, (size_t)RESULT_SLOTS * RESULT_SLOT_BYTES, cudaHostAllocDefault) != cudaSuccess) {
     delete m;
     return fail(BZ_ERR_NO_DEVICE, "pinned allocation failed");
@@ -464,7 +476,12 @@ extern "C" int32_t bz_msm_free(bz_msm* m) {
   ws_free(m);
   if (m->table) cudaFree(m->table);
   if (m->dma_points) cudaFree(m->dma_points);
-  if (m->scalars_dev) cudaFree(m->scalars_dev);
+  for (int b = 0; b < 2; b++) {
+    if (m->scalars_dev[b]) cudaFree(m->scalars_dev[b]);
+    if (m->ev_copied[b]) cudaEventDestroy(m->ev_copied[b]);
+    if (m->ev_consumed[b]) cudaEventDestroy(m->ev_consumed[b]);
+  }
+  if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
   if (m->pinned) cudaFreeHost(m->pinned);
   for (auto& e : m->ev) if (e) cudaEventDestroy(e);
   delete m;
@@ -529,8 +546,13 @@ static int32_t launch_task(bz_msm* m) {
   CUDA_TRY(BZ_ERR_UNKNOWN, cudaMemsetAsync(m->ws.err, 0, 4, st));
   m->ws.ev_acc0 = m->ev[2];
   m->ws.ev_acc1 = m->ev[3];
+  if (m->stage_cur >= 0) CUDA_TRY(BZ_ERR_UNKNOWN, cudaStreamWaitEvent(st, m->ev_copied[m->stage_cur], 0));
   cudaEventRecord(m->ev[0], st);
   launch_msm_sort(m->plan, m->ws, m->scalars_src, st);
+  if (m->stage_cur >= 0) {   // k_digits (the only reader of the staging buffer) is queued: mark it consumed
+    cudaEventRecord(m->ev_consumed[m->stage_cur], st);
+    m->consumed_valid[m->stage_cur] = true;
+  }
   cudaEventRecord(m->ev[1], st);
   m->ops->bucket_phase(m->plan, m->ws, m->table, st);
   cudaEventRecord(m->ev[4], st);
@@ -589,15 +611,25 @@ static int32_t ensure_arena_table(bz_msm* m, uint64_t addr, uint64_t n_points) {
 }
 
 static int32_t stage_scalars(bz_msm* m, const uint8_t* scalars, size_t len) {
-  if (m->scalars_cap < len) {
-    if (m->scalars_dev) cudaFree(m->scalars_dev);
-    m->scalars_dev = nullptr;
-    m->scalars_cap = 0;
-    CUDA_TRY(BZ_ERR_WRITE, cudaMalloc((void**)&m->scalars_dev, len));
-    m->scalars_cap = len;
+  const int b = m->stage_next;
+  m->stage_next ^= 1;
+  if (m->scalars_cap[b] < len) {
+    if (m->scalars_dev[b]) cudaFree(m->scalars_dev[b]);   // cudaFree waits for outstanding work
+    m->scalars_dev[b] = nullptr;
+    m->scalars_cap[b] = 0;
+    m->consumed_valid[b] = false;
+    CUDA_TRY(BZ_ERR_WRITE, cudaMalloc((void**)&m->scalars_dev[b], len));
+    m->scalars_cap[b] = len;
   }
-  CUDA_TRY(BZ_ERR_WRITE, cudaMemcpyAsync(m->scalars_dev, scalars, len, cudaMemcpyHostToDevice, m->dc->stream));
-  m->scalars_src = m->scalars_dev;
+  // do not overwrite the buffer before the task that used it last has read it
+  if (m->consumed_valid[b]) CUDA_TRY(BZ_ERR_WRITE, cudaStreamWaitEvent(m->copy_stream, m->ev_consumed[b], 0));
+  CUDA_TRY(BZ_ERR_WRITE, cudaMemcpyAsync(m->scalars_dev[b], scalars, len, cudaMemcpyHostToDevice, m->copy_stream));
+  CUDA_TRY(BZ_ERR_WRITE, cudaEventRecord(m->ev_copied[b], m->copy_stream));
+  // the caller may drop its buffer when we return (move-in semantics): block the HOST on the copy
+  // stream only -- the work stream keeps running the previous task meanwhile
+  CUDA_TRY(BZ_ERR_WRITE, cudaStreamSynchronize(m->copy_stream));
+  m->scalars_src = m->scalars_dev[b];
+  m->stage_cur = b;
   return BZ_OK;
 }
 
@@ -627,6 +659,7 @@ static int32_t set_data_common(bz_msm* m, const uint8_t* points, size_t points_l
       m->dma_points_cap = points_len;
     }
     CUDA_TRY(BZ_ERR_WRITE, cudaMemcpyAsync(m->dma_points, points, points_len, cudaMemcpyHostToDevice, m->dc->stream));
+    CUDA_TRY(BZ_ERR_WRITE, cudaStreamSynchronize(m->dc->stream));   // the caller may drop `points` on return
     rc = build_table(m, m->dma_points, npts);
     if (rc) return rc;
     m->table_from_arena = false;
@@ -644,9 +677,8 @@ static int32_t set_data_common(bz_msm* m, const uint8_t* points, size_t points_l
   if (scalars_host) {
     rc = stage_scalars(m, scalars_host, scalars_len);
     if (rc) return rc;
-    // the caller may drop its buffers when we return (move-in semantics)
-    CUDA_TRY(BZ_ERR_WRITE, cudaStreamSynchronize(m->dc->stream));
   } else {
+    m->stage_cur = -1;
     m->scalars_src = reinterpret_cast<const uint32_t*>(scalars_dev_ptr);
   }
   m->data_M = npts;
