@@ -369,6 +369,8 @@ static int32_t make_plan(bz_msm* m, uint64_t M, int words_per_scalar) {
     if (cost < best) { best = cost; best_c = c; }
   }
   if (!best_c) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "no feasible window size for %llu elements", (unsigned long long)M);
+  p.batch_affine = 0;
+  if (const char* e = getenv("BZ_MSM_BA")) p.batch_affine = atoi(e) ? 1 : 0;
   p.c = best_c;
   p.W = plan_windows(smax, sbits, p.c, p.dc);
   p.nb = (1u << (p.c - 1)) + 1;
@@ -420,6 +422,23 @@ static int32_t make_plan(bz_msm* m, uint64_t M, int words_per_scalar) {
     A((uint8_t**)&m->ws.part2_pt, (size_t)tot * 2 * xb);
   }
   A(&m->ws.wbase, (size_t)(p.W + 1) * 4);
+  if (p.batch_affine) {
+    const size_t fb = (size_t)m->ops->fq_bytes, ab = m->ops->affine_bytes;
+    const uint64_t ng = (uint64_t)p.W * p.nb;
+    const uint64_t S1 = (total >> 1) + ng, S2 = (total >> 2) + ng;
+    const uint64_t n0 = ((S1 + 511) / 512) * 32 + 256, n1 = n0 / 256 + 2, n2 = n1 / 256 + 2, n3 = n2 / 256 + 2;
+    A(&m->ws.ba_scalars, 16);
+    A(&m->ws.ba_pref, S1 * fb);
+    A(&m->ws.ba_tot, n0 * fb);
+    A(&m->ws.ba_itot, n0 * fb);
+    A(&m->ws.ba_lvl[0], n1 * fb);
+    A(&m->ws.ba_lvlp[0], n1 * fb);
+    A(&m->ws.ba_lvl[1], n2 * fb);
+    A(&m->ws.ba_lvlp[1], n2 * fb);
+    A(&m->ws.ba_lvl[2], n3 * fb);
+    A((uint8_t**)&m->ws.ba_buf1, S1 * ab);
+    A((uint8_t**)&m->ws.ba_buf0, S2 * ab);
+  }
   A((uint8_t**)&m->ws.red_a, (size_t)2 * p.W * p.nchunks * xb);        // S and V of the even levels
   A((uint8_t**)&m->ws.red_b, (size_t)2 * p.W * (nch1 + 1) * xb);       // ... of the odd levels
   A(&m->ws.err, 16);

@@ -132,6 +132,41 @@ struct ec {
     acc.Y = Y3;
   }
 
+  // ---- affine + affine with a shared ("batched") inversion --------------------------------------
+  // ba_classify picks the denominator whose inverse the addition needs and says which formula applies;
+  // ba_finish completes the addition given that inverse.  Denominators are never zero, so thousands of
+  // them can be inverted with one field inversion (Montgomery's trick, see msm_ba.cuh).
+  //   kind 0: generic chord          den = x2 - x1     lambda = (y2 - y1) / den
+  //   kind 1: tangent (p1 == p2)     den = 2 y1        lambda = 3 x1^2 / den
+  //   kind 2: p1 is the identity     den = 1           result = p2
+  //   kind 3: p2 is the identity     den = 1           result = p1
+  //   kind 4: p1 == -p2              den = 1           result = identity (encoded (0, 0))
+  BZ_HDI static int ba_classify(const A& p1, const A& p2, E& den) {
+    if (is_identity(p1)) { den = F::one(); return 2; }
+    if (is_identity(p2)) { den = F::one(); return 3; }
+    E dx = F::sub(p2.x, p1.x);
+    if (!F::is_zero(dx)) { den = dx; return 0; }
+    if (F::is_zero(F::add(p1.y, p2.y))) { den = F::one(); return 4; }   // also covers y == 0
+    den = F::dbl(p1.y);
+    return 1;
+  }
+  BZ_HDI static A ba_finish(int kind, const A& p1, const A& p2, const E& inv_den) {
+    if (kind == 2) return p2;
+    if (kind == 3) return p1;
+    A r;
+    if (kind == 4) { r.x = F::zero(); r.y = F::zero(); return r; }
+    E lam;
+    if (kind == 0) {
+      lam = F::mul(F::sub(p2.y, p1.y), inv_den);
+    } else {
+      E x2 = F::sqr(p1.x);
+      lam = F::mul(F::add(F::dbl(x2), x2), inv_den);
+    }
+    r.x = F::sub(F::sub(F::sqr(lam), p1.x), p2.x);
+    r.y = F::sub(F::mul(lam, F::sub(p1.x, r.x)), p1.y);
+    return r;
+  }
+
   BZ_HDI static A neg(const A& a) {
     A r;
     r.x = a.x;

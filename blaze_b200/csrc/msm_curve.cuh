@@ -380,6 +380,9 @@ __global__ void k_field_selftest(const uint8_t* __restrict__ a, const uint8_t* _
 
 // ---------------------------------------------------------------------------------------------
 template <class C>
+static void ba_bucket_phase_fwd(const MsmPlan& p, const MsmWorkspace& ws, const void* table, cudaStream_t st);   // msm_ba.cuh
+
+template <class C>
 struct CurveLaunch {
   static void points_to_mont(const uint8_t* raw, void* table, uint64_t n, cudaStream_t st) {
     if (!n) return;
@@ -389,7 +392,10 @@ struct CurveLaunch {
   static void bucket_phase(const MsmPlan& p, const MsmWorkspace& ws, const void* table, cudaStream_t st) {
     const uint32_t ngoff = (uint32_t)p.W * p.nb;
     XyzzM<C>* buckets = (XyzzM<C>*)ws.buckets;
-    cudaMemsetAsync(buckets, 0, (size_t)ngoff * sizeof(XyzzM<C>), st);
+    if (!p.batch_affine) cudaMemsetAsync(buckets, 0, (size_t)ngoff * sizeof(XyzzM<C>), st);
+    if (p.batch_affine) {
+      ba_bucket_phase_fwd<C>(p, ws, table, st);
+    } else {
     if (ws.ev_acc0) cudaEventRecord(ws.ev_acc0, st);
     k_accumulate<C><<<(unsigned)((p.nseg + 127) / 128), 128, 0, st>>>(
         (const AffineM<C>*)table, ws.sorted, ws.goff, buckets, ws.part_id, (XyzzM<C>*)ws.part_pt, p.nseg, p.seg_len,
@@ -418,6 +424,7 @@ struct CurveLaunch {
         span *= group;
       }
     }
+    }   // !batch_affine
     // multi-level running-sum reduction (see k_reduce_level); scratch: red_a = S / V of even levels, red_b = odd
     g_kernel_launches += 2;   // accumulate, finish
     const uint32_t s = p.chunk;

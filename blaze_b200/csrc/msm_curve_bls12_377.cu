@@ -1,5 +1,6 @@
 // Bls12_377 instantiation of the MSM back end (see msm_curve.cuh).
 #include "msm_curve.cuh"
+#include "msm_ba.cuh"
 
 namespace bz {
 template <>

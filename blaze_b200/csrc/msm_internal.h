@@ -38,6 +38,7 @@ struct MsmPlan {
   uint32_t tile, ntiles;   // level-1 tile size / count
   uint32_t seg_len;        // sorted entries per accumulate thread
   uint64_t nseg;           // number of accumulate segments = ceil(W*M / seg_len)
+  int batch_affine;        // 1: accumulate buckets by batched affine addition (msm_ba.cuh), 0: XYZZ sweep
   uint32_t chunk;          // entries per reduce thread at every level of the running-sum recursion (power of two)
   uint32_t nchunks;        // ceil(nb / chunk): level-0 chunk count
   DigitConst dc;
@@ -61,6 +62,15 @@ struct MsmWorkspace {
   void* red_b;         // ... of the odd levels
   int* err;            // device error flag
   uint8_t* result;     // 3*FQ_BYTES result record (device)
+  // batched-affine accumulation (msm_ba.cuh); null when that mode is off
+  uint32_t* ba_scalars;           // [4] device scratch words
+  uint32_t* ba_pref;              // running denominator products, one field element per output slot
+  uint32_t* ba_tot;               // per-thread totals, then ba_itot = their inverses
+  uint32_t* ba_itot;
+  uint32_t* ba_lvl[3];            // batch-inverse tree: group products per level
+  uint32_t* ba_lvlp[2];           //                      prefix / inverse arrays per level
+  void* ba_buf0;                  // affine lists of the even rounds (>= 2): (total/4 + W nb) entries
+  void* ba_buf1;                  // affine lists of the odd rounds: (total/2 + W nb) entries
   cudaEvent_t ev_acc0, ev_acc1;   // bracket the accumulate kernel alone (roofline timing); may be null
 };
 

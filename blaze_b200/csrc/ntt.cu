@@ -109,19 +109,19 @@ __global__ void k_ntt_tables(uint4* lo, uint4* hi, uint4* ninv, int log_root, in
 
 // ---------------------------------------------------------------------------------------------
 template <class F, int B>   // one in-place DIF round of radix 2^B on the shared tile
-__device__ __forceinline__ void dif_round(uint4* lo, uint4* hi, const uint4* trl, const uint4* trh, int lr,
+__device__ __forceinline__ void dif_round(uint4* lo, uint4* hi, const uint4* trl, const uint4* trh, int lr, int lv,
                                           int lblk /*log2 of the current block size*/, int tid, int nthreads) {
   typedef ff<F> A;
   typedef Fe<F> E;
   constexpr int RHO = 1 << B;
-  constexpr int V = NTT_LANES;
+  const int V = 1 << lv;
   const int R = 1 << lr;
   const int lsub = lblk - B;
   const int sub = 1 << lsub;            // stride between the points of one butterfly group
   const int items = V * (R / RHO);
   const int tws = R >> lblk;            // w_blk = w_R^tws
   for (int w = tid; w < items; w += nthreads) {
-    int v = w % V, grp = w / V;
+    int v = w & (V - 1), grp = w >> lv;
     int b0 = grp >> lsub, u = grp & (sub - 1);
     int base = (b0 << lblk) + u;
     E x[RHO];
@@ -163,13 +163,13 @@ __global__ void __launch_bounds__(256, 2) k_ntt_pass(NttPassParams P) {
   typedef ff<F> A;
   typedef Fe<F> E;
   extern __shared__ uint4 smem[];
-  const int R = 1 << P.lr, V = NTT_LANES;
+  const int R = 1 << P.lr, V = 1 << P.lv;
   uint4* lo = smem;
   uint4* hi = smem + R * V;
   uint4* trl = smem + 2 * R * V;   // w_R^e table, lo halves
   uint4* trh = trl + R;
   const int tid = threadIdx.x, nth = blockDim.x;
-  const uint64_t qbase = (uint64_t)blockIdx.x * V;
+  const uint64_t qbase = (uint64_t)blockIdx.x << P.lv;
 
   // w_R^e = w^(e * root/R)
   for (int e = tid; e < R; e += nth) {
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(256, 2) k_ntt_pass(NttPassParams P) {
   }
   // load (lane fastest: V adjacent work items are adjacent in memory), apply the pass twiddle
   for (int idx = tid; idx < R * V; idx += nth) {
-    int v = idx & (V - 1), r = idx / V;
+    int v = idx & (V - 1), r = idx >> P.lv;
     uint64_t q = qbase + v;
     if (q >= P.Q) continue;
     uint64_t q0 = q & (P.Q0 - 1), qr = q >> P.lq0;
@@ -194,14 +194,14 @@ __global__ void __launch_bounds__(256, 2) k_ntt_pass(NttPassParams P) {
   __syncthreads();
   // DIF rounds: radix 8 while possible, then 4 or 2
   int lblk = P.lr, rem = P.lr;
-  while (rem >= 3) { dif_round<F, 3>(lo, hi, trl, trh, P.lr, lblk, tid, nth); lblk -= 3; rem -= 3; __syncthreads(); }
-  if (rem == 2) { dif_round<F, 2>(lo, hi, trl, trh, P.lr, lblk, tid, nth); __syncthreads(); }
-  if (rem == 1) { dif_round<F, 1>(lo, hi, trl, trh, P.lr, lblk, tid, nth); __syncthreads(); }
+  while (rem >= 3) { dif_round<F, 3>(lo, hi, trl, trh, P.lr, P.lv, lblk, tid, nth); lblk -= 3; rem -= 3; __syncthreads(); }
+  if (rem == 2) { dif_round<F, 2>(lo, hi, trl, trh, P.lr, P.lv, lblk, tid, nth); __syncthreads(); }
+  if (rem == 1) { dif_round<F, 1>(lo, hi, trl, trh, P.lr, P.lv, lblk, tid, nth); __syncthreads(); }
   // store: position p holds X[k], k = digit reversal of p over the round radices
   const int n8 = P.lr / 3, last = P.lr % 3;
   for (int idx = tid; idx < R * V; idx += nth) {
     int v, k;
-    if (P.store_k_fastest) { k = idx & (R - 1); v = idx >> P.lr; } else { v = idx % V; k = idx / V; }
+    if (P.store_k_fastest) { k = idx & (R - 1); v = idx >> P.lr; } else { v = idx & (V - 1); k = idx >> P.lv; }
     uint64_t q = qbase + v;
     if (q >= P.Q) continue;
     // p from k: k = m1 + 8 m2 + 64 m3 (+ ...), p = m1 R/8 + m2 R/64 + ...
@@ -241,16 +241,20 @@ static void gen_tables_t(NttTables& t, int log_root, int inverse, cudaStream_t s
 }
 
 template <class F>
-static cudaError_t launch_pass_t(const NttPassParams& P, cudaStream_t st) {
+static cudaError_t launch_pass_t(const NttPassParams& Pin, cudaStream_t st) {
+  NttPassParams P = Pin;
   int R = 1 << P.lr;
-  size_t smem = ((size_t)2 * R * NTT_LANES + 2 * R) * sizeof(uint4);
+  int V = NTT_TILE / R < 4 ? 4 : NTT_TILE / R;
+  P.lv = 0;
+  while ((1 << P.lv) < V) P.lv++;
+  size_t smem = ((size_t)2 * R * V + 2 * R) * sizeof(uint4);
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(k_ntt_pass<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = smem;
   }
-  uint64_t ctas = (P.Q + NTT_LANES - 1) / NTT_LANES;
+  uint64_t ctas = (P.Q + V - 1) / V;
   k_ntt_pass<F><<<(unsigned)ctas, 256, smem, st>>>(P);
   g_kernel_launches += 1;
   return cudaGetLastError();

@@ -6,7 +6,7 @@
 
 namespace bz {
 
-#define NTT_LANES 4          // adjacent work items per CTA (4 x 32 B = 128-byte global runs = one cache line)
+#define NTT_TILE 2048         // elements per CTA tile: lanes V = NTT_TILE / R adjacent work items (>= 4, i.e. >= 128-byte runs)
 #define NTT_MAX_PEERS 8
 
 struct NttTables {
@@ -29,6 +29,7 @@ struct NttPassParams {
   uint32_t peer_rows;               // 0 = not an exchange pass; else a power of two
   int lpeer_rows;
   int lr;                           // log2 of the pass radix R (1..9)
+  int lv;                           // log2 of the lanes per CTA, V = max(4, NTT_TILE / R) (set by ntt_launch_pass)
   uint64_t Q;
   uint64_t Q0, Q1;                  // powers of two
   int lq0, lq1;                     // their logs (index split by shift/mask, no 64-bit division)

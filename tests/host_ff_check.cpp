@@ -66,6 +66,15 @@ static int curve_op(int op, const uint8_t* p, const uint8_t* q, uint32_t k1, uin
     E::madd(acc, E::neg(b));
     XYZZ<C> t = acc;
     E::add(acc, t);
+  } else if (op == 3) {   // batched-affine building blocks: classify, invert the denominator, finish
+    typename E::E den;
+    int kind = E::ba_classify(a, b, den);
+    Affine<C> r3 = E::ba_finish(kind, a, b, ff<typename C::Fq>::inv(den));
+    memset(out, 0, 2 * C::FQ_BYTES);
+    if (E::is_identity(r3)) return 1;
+    store<typename C::Fq>(out, r3.x, C::FQ_BYTES);
+    store<typename C::Fq>(out + C::FQ_BYTES, r3.y, C::FQ_BYTES);
+    return 0;
   } else {
     return -1;
   }
