@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--cpu-sample-log-n", type=int, default=18)
     ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--curve", default="BLS381", choices=["BLS381", "BLS377", "BN254"],
+                    help="headline metric is BLS381; the other curves run the same workload (e.g. configs[4])")
     ap.add_argument("--no-ntt", action="store_true", help="skip the secondary metric (2^27 NTT ms)")
     ap.add_argument("--ntt-log-n", type=int, default=27)
     return ap.parse_args()
@@ -252,12 +254,13 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    c = curves.BLS12_381
+    cname = {"BLS381": "BLS12_381", "BLS377": "BLS12_377", "BN254": "BN254"}[args.curve]
+    c = curves.CURVES[cname]
     N = 1 << args.log_n
     per = N // world
     first = rank * per
     dc = bz.DriverClient(str(local), bz.DriverConfig.driver_client_cfg(bz.CardType.B200))
-    m = bz.MSMClient.new(bz.MSMInit(bz.PointMemoryType.HBM, False, bz.Curve.BLS381), dc)
+    m = bz.MSMClient.new(bz.MSMInit(bz.PointMemoryType.HBM, False, getattr(bz.Curve, args.curve)), dc)
     p0, q = seed_points(c, 2026)
     HBM_ADDR = 0
     # resident points: P_i = P0 + i*Q for this rank's index range, generated on the device (untimed)
@@ -310,7 +313,7 @@ def main():
         from oracle import capi
         capi.build()
         full_sc = random_scalars(c, N, seed=4242)
-        exp = capi.chain_expected("BLS12_381", p0, q, full_sc, N)
+        exp = capi.chain_expected(cname, p0, q, full_sc, N)
         verified = bool(res == exp)
         if not verified:
             raise SystemExit("bench: GPU result differs from the oracle closed form -- number is INVALID")
@@ -397,13 +400,14 @@ def main():
             except Exception:
                 traffic = None
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": METRIC if args.curve == "BLS381" else METRIC.replace("BLS12-381", cname.replace("_", "-")),
+            "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "u32 limbs (381-bit Fq Montgomery, 255-bit Fr)",
             "data": "synthetic",
             "config": {
-                "workload": "BLS12-381 MSM 2^%d, HBM-resident points (configs[1]); points P0+iQ generated on device, "
-                            "uniform random canonical scalars" % args.log_n,
+                "workload": "%s MSM 2^%d, HBM-resident points (configs[1]); points P0+iQ generated on device, "
+                            "uniform random canonical scalars" % (cname.replace("_", "-"), args.log_n),
                 "precompute_factor": 1, "window_bits": cbits, "windows": W, "segment": plan["segment"],
                 "parallelism": "point-sharded x%d" % world,
                 "l2": "inputs (2 GiB scalars + 6 GiB points per 2^26) exceed the 126 MB L2; no flush needed",
@@ -419,7 +423,7 @@ def main():
                     "serial_ms_per_step": 1e3 * wall_e2e_serial / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_accumulate<Bls12_381>", "achieved": achieved, "peak": hbm_peak,
+            "roofline": {"bound": "hbm", "kernel": "k_accumulate<%s>" % cname, "achieved": achieved, "peak": hbm_peak,
                          "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes,

@@ -373,17 +373,20 @@ static int32_t make_plan(bz_msm* m, uint64_t M, int words_per_scalar) {
   if (const char* e = getenv("BZ_MSM_BA")) p.batch_affine = atoi(e) ? 1 : 0;
   p.c = best_c;
   p.W = plan_windows(smax, sbits, p.c, p.dc);
-  p.nb = (1u << (p.c - 1)) + 1;
-  // level-2 (fine) bits: a coarse bin should hold ~32K entries (measured best at 2^26) so that the CTA that sorts it owns a
+  p.nvalues = (1u << (p.c - 1)) + 1;
+  // level-2 (fine) bits: a coarse bin should hold ~32K entries so that the CTA that sorts it owns a
   // small, quickly-filled output window (L2 merges its 4-byte scatter writes into full sectors)
   {
     int f = 1;
     while (f < 10 && f < p.c - 1 && ((double)M / (double)(1ull << (p.c - 1 - (f + 1)))) <= 32768.0) f++;
     p.fbits = std::max(1, std::min(f, p.c - 1));
-    while (((p.nb - 1) >> p.fbits) + 1 > 8193) p.fbits++;   // level-1 histogram must fit shared memory
-    if (const char* e = getenv("BZ_MSM_FBITS")) { int v = atoi(e); if (v >= 1 && v <= 12 && v < p.c) p.fbits = v; }
+    while (p.c - 1 - p.fbits > 13) p.fbits++;   // level-1 histogram (2^cbits counters) must fit shared memory
+    if (const char* e = getenv("BZ_MSM_FBITS")) { int v = atoi(e); if (v >= 1 && v <= 12 && v < p.c && p.c - 1 - v <= 13) p.fbits = v; }
   }
-  p.ncoarse = (int)(((p.nb - 1) >> p.fbits) + 1);
+  p.cbits = p.c - 1 - p.fbits;
+  p.ncoarse = 1 << p.cbits;
+  p.nfine = (1u << p.fbits) + 1;
+  p.nb = (uint32_t)p.ncoarse * p.nfine;
   p.tile = 65536;
   p.ntiles = (uint32_t)((M + p.tile - 1) / p.tile);
   uint64_t total = (uint64_t)p.W * M;
@@ -394,12 +397,12 @@ static int32_t make_plan(bz_msm* m, uint64_t M, int words_per_scalar) {
   p.seg_len = L;
   p.nseg = (total + L - 1) / L;
   // reduction chunk (k_reduce_level): 16 buckets per thread, 8 when that leaves the machine underfilled
-  p.chunk = ((uint64_t)p.W * p.nb / 16 < 148ull * 256) ? 8 : 16;
+  p.chunk = ((uint64_t)p.W * p.nvalues / 16 < 148ull * 256) ? 8 : 16;
   if (const char* e = getenv("BZ_MSM_CHUNK")) {
     uint32_t ch = (uint32_t)atoi(e);
     if (ch >= 2 && (ch & (ch - 1)) == 0 && ch <= 1024) p.chunk = ch;
   }
-  p.nchunks = (p.nb + p.chunk - 1) / p.chunk;
+  p.nchunks = (p.nvalues + p.chunk - 1) / p.chunk;
   uint32_t nch1 = (p.nchunks + p.chunk - 1) / p.chunk;
 
   size_t xb = m->ops->xyzz_bytes;
@@ -816,7 +819,7 @@ extern "C" int32_t bz_msm_plan_info(bz_msm* m, uint32_t out[4]) {
   if (!m || !out) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null argument");
   out[0] = m->have_plan ? m->plan.c : 0;
   out[1] = m->have_plan ? m->plan.W : 0;
-  out[2] = m->have_plan ? m->plan.nb : 0;
+  out[2] = m->have_plan ? m->plan.nvalues : 0;
   out[3] = m->have_plan ? m->plan.seg_len : 0;
   return BZ_OK;
 }

@@ -251,25 +251,28 @@ __global__ void __launch_bounds__(128) k_merge_level(const uint32_t* __restrict_
 // so the window total is the single V of the top level.
 template <class C>
 __global__ void __launch_bounds__(128, 2)
-k_reduce_level(const XyzzM<C>* __restrict__ A, const XyzzM<C>* __restrict__ Vin, uint32_t n, uint32_t s,
-               uint32_t nchunks, int W, int level_shift /* l * log2(s) */, XyzzM<C>* __restrict__ Sout,
-               XyzzM<C>* __restrict__ Vout) {
+k_reduce_level(const XyzzM<C>* __restrict__ A, const XyzzM<C>* __restrict__ Vin, uint32_t n, uint32_t a_stride,
+               int cbits /* >= 0: entry i lives in slot (i & (2^cbits - 1)) * nfine + (i >> cbits) */, uint32_t nfine,
+               uint32_t s, uint32_t nchunks, int W, int level_shift /* l * log2(s) */,
+               XyzzM<C>* __restrict__ Sout, XyzzM<C>* __restrict__ Vout) {
   typedef dev<C> D;
   typedef ec<C> G;
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (uint32_t)W * nchunks) return;
   uint32_t w = t / nchunks, k = t % nchunks;
-  const XyzzM<C>* a = A + (uint64_t)w * n;
+  const XyzzM<C>* a = A + (uint64_t)w * a_stride;
+  const uint32_t cmask = cbits >= 0 ? (1u << cbits) - 1 : 0;
+  auto slot = [&](uint32_t i) { return cbits >= 0 ? (i & cmask) * nfine + (i >> cbits) : i; };
   uint32_t lo = k * s, hi = lo + s;
   if (hi > n) hi = n;
   XYZZ<C> S = G::infinity(), R = G::infinity();
   for (uint32_t i = hi - 1; i > lo; i--) {
-    XYZZ<C> v = D::load_xyzz(a + i);
+    XYZZ<C> v = D::load_xyzz(a + slot(i));
     G::add(S, v);
     G::add(R, S);
   }
   {
-    XYZZ<C> v = D::load_xyzz(a + lo);
+    XYZZ<C> v = D::load_xyzz(a + slot(lo));
     G::add(S, v);
   }
   for (int d = 0; d < level_shift; d++) R = G::dbl(R);
@@ -432,7 +435,8 @@ struct CurveLaunch {
     while ((1u << log_s) < s) log_s++;
     const XyzzM<C>* A = buckets;
     const XyzzM<C>* Vin = nullptr;
-    uint32_t n = p.nb;
+    uint32_t n = p.nvalues, a_stride = p.nb;
+    int perm_bits = p.cbits;
     XyzzM<C>* scratch[2] = {(XyzzM<C>*)ws.red_a, (XyzzM<C>*)ws.red_b};
     int level = 0;
     const XyzzM<C>* top = nullptr;
@@ -441,13 +445,16 @@ struct CurveLaunch {
       XyzzM<C>* Sout = scratch[level & 1];
       XyzzM<C>* Vout = Sout + (size_t)p.W * nch;
       uint32_t nt = (uint32_t)p.W * nch;
-      k_reduce_level<C><<<(nt + 127) / 128, 128, 0, st>>>(A, Vin, n, s, nch, p.W, level * log_s, Sout, Vout);
+      k_reduce_level<C><<<(nt + 127) / 128, 128, 0, st>>>(A, Vin, n, a_stride, perm_bits, p.nfine, s, nch, p.W,
+                                                        level * log_s, Sout, Vout);
       g_kernel_launches += 1;
       top = Vout;
       if (nch == 1) break;
       A = Sout;
       Vin = Vout;
       n = nch;
+      a_stride = nch;
+      perm_bits = -1;
       level++;
     }
     k_finish<C><<<1, 32, 0, st>>>(top, p.W, p.c, ws.result);

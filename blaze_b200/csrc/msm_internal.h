@@ -32,9 +32,16 @@ struct MsmPlan {
   int words_per_scalar;    // 8: full 256-bit scalars; 1: 32-bit limbs against a x8 precomputed table
   int c;                   // window bits
   int W;                   // number of windows
-  uint32_t nb;             // buckets per window = 2^(c-1) + 1 (bucket 0 is never accumulated)
+  // Bucket VALUES per window are 0 .. 2^(c-1) (nvalues of them; value 0 is never accumulated).  The
+  // sort splits a value b into coarse = b & (ncoarse-1) (LOW bits: level 1) and fine = b >> cbits (level
+  // 2), so skewed digit ranges -- small scalars, a short top window -- still spread over all coarse
+  // bins.  Bucket SLOT of value b is coarse * nfine + fine; nb = ncoarse * nfine slots per window.
+  uint32_t nvalues;        // 2^(c-1) + 1
+  uint32_t nb;             // bucket slots per window = ncoarse * nfine (>= nvalues, the extra ones stay empty)
   int fbits;               // level-2 (fine) sort bits
-  int ncoarse;             // level-1 bins = ((nb-1) >> fbits) + 1
+  int cbits;               // level-1 (coarse) bits = c - 1 - fbits
+  int ncoarse;             // level-1 bins = 2^cbits
+  uint32_t nfine;          // level-2 bins = 2^fbits + 1 (the +1 holds the single value 2^(c-1))
   uint32_t tile, ntiles;   // level-1 tile size / count
   uint32_t seg_len;        // sorted entries per accumulate thread
   uint64_t nseg;           // number of accumulate segments = ceil(W*M / seg_len)

@@ -7,7 +7,7 @@
 // Data flow (M = number of (sub)scalars, W windows of c bits, nb = 2^(c-1)+1 buckets/window):
 //   scalars (32 B or 4 B each, read ONCE, coalesced)
 //     -> k_digits      dig[w][i]   = sign<<31 | |digit|                       (4 B x W x M)
-//     -> k_hist1       hmat[w][tile][coarse] tile histograms of the top bits  (no atomics to HBM)
+//     -> k_hist1       hmat[w][tile][coarse] tile histograms of the LOW bucket bits (no atomics to HBM)
 //     -> k_colscan1 / k_binscan1  exclusive prefix over tiles, then over coarse bins
 //     -> k_scatter1    l1[w][pos]  = {bucket, sign|idx} grouped by coarse bin (8 B x W x M)
 //     -> k_sort2       sorted[w*M + pos] = sign|idx grouped by bucket, and
@@ -81,8 +81,9 @@ __global__ void __launch_bounds__(256) k_digits(const uint32_t* __restrict__ sca
 }
 
 // ---------------------------------------------------------------------------------------------
-// level 1: group by coarse bin = bucket >> fbits
-__global__ void __launch_bounds__(512) k_hist1(const uint32_t* __restrict__ dig, uint64_t M, int fbits, int ncoarse,
+// level 1: group by coarse bin = bucket & (ncoarse - 1).  Low bits, not high bits: a window whose digits
+// only span a few bits (short top window, small scalars) would otherwise land in ONE coarse bin.
+__global__ void __launch_bounds__(512) k_hist1(const uint32_t* __restrict__ dig, uint64_t M, uint32_t cmask, int ncoarse,
                                                uint32_t tile, uint32_t ntiles, uint32_t* __restrict__ hmat) {
   extern __shared__ uint32_t sh[];
   int w = blockIdx.y;
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(512) k_hist1(const uint32_t* __restrict__ dig,
   const uint32_t* d = dig + (uint64_t)w * M;
   for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
     uint32_t b = __ldg(d + i) & 0x7fffffffu;
-    if (b) atomicAdd(&sh[b >> fbits], 1u);   // zero digits contribute nothing: dropped here
+    if (b) atomicAdd(&sh[b & cmask], 1u);   // zero digits contribute nothing: dropped here
   }
   __syncthreads();
   uint32_t* out = hmat + ((uint64_t)w * ntiles + t) * ncoarse;
@@ -158,7 +159,7 @@ __global__ void k_wbase(const uint32_t* __restrict__ base1, int ncoarse, int W, 
   *goff_end = run;
 }
 
-__global__ void __launch_bounds__(512) k_scatter1(const uint32_t* __restrict__ dig, uint64_t M, int fbits, int ncoarse,
+__global__ void __launch_bounds__(512) k_scatter1(const uint32_t* __restrict__ dig, uint64_t M, uint32_t cmask, int ncoarse,
                                                   uint32_t tile, uint32_t ntiles, const uint32_t* __restrict__ hmat,
                                                   const uint32_t* __restrict__ base1, uint2* __restrict__ l1) {
   extern __shared__ uint32_t sh[];
@@ -176,19 +177,19 @@ __global__ void __launch_bounds__(512) k_scatter1(const uint32_t* __restrict__ d
     uint32_t e = __ldg(d + i);
     uint32_t b = e & 0x7fffffffu;
     if (!b) continue;
-    uint32_t pos = atomicAdd(&sh[b >> fbits], 1u);
+    uint32_t pos = atomicAdd(&sh[b & cmask], 1u);
     out[pos] = make_uint2(b, (e & 0x80000000u) | (uint32_t)i);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// level 2: one block per (coarse bin, window): counting sort by the low fbits of the bucket
-__global__ void __launch_bounds__(256) k_sort2(const uint2* __restrict__ l1, uint64_t M, int fbits, int ncoarse,
-                                               uint32_t nb, int W, const uint32_t* __restrict__ base1,
+// level 2: one block per (coarse bin, window): counting sort by the high bits (bucket >> cbits)
+__global__ void __launch_bounds__(256) k_sort2(const uint2* __restrict__ l1, uint64_t M, int cbits, int ncoarse,
+                                               uint32_t nfine_, uint32_t nb, int W, const uint32_t* __restrict__ base1,
                                                const uint32_t* __restrict__ wbase_arr,
                                                uint32_t* __restrict__ sorted, uint32_t* __restrict__ goff) {
   extern __shared__ uint32_t sh[];   // [nfine] counters, then [256] scan scratch
-  const int nfine = 1 << fbits;
+  const int nfine = (int)nfine_;
   uint32_t* cnt = sh;
   uint32_t* scratch = sh + nfine;
   int w = blockIdx.y;
@@ -196,10 +197,9 @@ __global__ void __launch_bounds__(256) k_sort2(const uint2* __restrict__ l1, uin
   const uint32_t* b1 = base1 + (uint64_t)w * (ncoarse + 1);
   uint32_t lo = b1[cb], hi = b1[cb + 1];
   const uint2* in = l1 + (uint64_t)w * M;
-  const uint32_t fmask = nfine - 1;
   for (int k = threadIdx.x; k < nfine; k += blockDim.x) cnt[k] = 0;
   __syncthreads();
-  for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(&cnt[in[i].x & fmask], 1u);
+  for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(&cnt[in[i].x >> cbits], 1u);
   __syncthreads();
   // exclusive scan of cnt[0..nfine): each thread owns a contiguous run
   int per = (nfine + blockDim.x - 1) / blockDim.x;
@@ -219,15 +219,14 @@ __global__ void __launch_bounds__(256) k_sort2(const uint2* __restrict__ l1, uin
   for (int k = klo; k < khi; k++) {
     uint32_t v = cnt[k];
     cnt[k] = run;   // becomes the scatter cursor
-    uint32_t b = ((uint32_t)cb << fbits) + k;
-    if (b < nb) goff[(uint64_t)w * nb + b] = (uint32_t)(wbase + run);
+    goff[(uint64_t)w * nb + (uint32_t)cb * nfine + k] = (uint32_t)(wbase + run);   // slot = coarse * nfine + fine
     run += v;
   }
   __syncthreads();
   uint32_t* out = sorted + wbase;
   for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
     uint2 e = in[i];
-    uint32_t pos = atomicAdd(&cnt[e.x & fmask], 1u);
+    uint32_t pos = atomicAdd(&cnt[e.x >> cbits], 1u);
     out[pos] = e.y;
   }
 }
@@ -241,17 +240,17 @@ void launch_msm_sort(const MsmPlan& p, const MsmWorkspace& ws, const uint32_t* s
   }
   dim3 g1(p.ntiles, p.W);
   size_t sh1 = (size_t)p.ncoarse * sizeof(uint32_t);
-  k_hist1<<<g1, 512, sh1, st>>>(ws.dig, M, p.fbits, p.ncoarse, p.tile, p.ntiles, ws.hmat);
+  k_hist1<<<g1, 512, sh1, st>>>(ws.dig, M, (uint32_t)p.ncoarse - 1, p.ncoarse, p.tile, p.ntiles, ws.hmat);
   {
     int n = p.W * p.ncoarse;
     k_colscan1<<<(n + 255) / 256, 256, 0, st>>>(ws.hmat, p.ntiles, p.ncoarse, p.W, ws.tot);
     k_binscan1<<<p.W, 1024, 0, st>>>(ws.tot, p.ncoarse, ws.base1);
     k_wbase<<<1, 32, 0, st>>>(ws.base1, p.ncoarse, p.W, ws.wbase, ws.goff + (size_t)p.W * p.nb);
   }
-  k_scatter1<<<g1, 512, sh1, st>>>(ws.dig, M, p.fbits, p.ncoarse, p.tile, p.ntiles, ws.hmat, ws.base1, ws.l1);
+  k_scatter1<<<g1, 512, sh1, st>>>(ws.dig, M, (uint32_t)p.ncoarse - 1, p.ncoarse, p.tile, p.ntiles, ws.hmat, ws.base1, ws.l1);
   dim3 g2(p.ncoarse, p.W);
-  size_t sh2 = ((size_t)(1u << p.fbits) + 256) * sizeof(uint32_t);
-  k_sort2<<<g2, 256, sh2, st>>>(ws.l1, M, p.fbits, p.ncoarse, p.nb, p.W, ws.base1, ws.wbase, ws.sorted, ws.goff);
+  size_t sh2 = ((size_t)p.nfine + 256) * sizeof(uint32_t);
+  k_sort2<<<g2, 256, sh2, st>>>(ws.l1, M, p.cbits, p.ncoarse, p.nfine, p.nb, p.W, ws.base1, ws.wbase, ws.sorted, ws.goff);
   g_kernel_launches += 7;
 }
 

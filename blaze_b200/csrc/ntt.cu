@@ -183,14 +183,23 @@ __global__ void __launch_bounds__(256, 2) k_ntt_pass(NttPassParams P) {
     if (q >= P.Q) continue;
     uint64_t q0 = q & (P.Q0 - 1), qr = q >> P.lq0;
     uint64_t q1 = qr & (P.Q1 - 1), q2 = qr >> P.lq1;
-    const uint4* src = P.in + 2 * (q0 * P.in_s0 + q1 * P.in_s1 + q2 * P.in_s2 + (uint64_t)r * P.in_sr);
-    E x = nt<F>::ld(src);
+    const uint64_t off = q0 * P.in_s0 + q1 * P.in_s1 + q2 * P.in_s2 + (uint64_t)r * P.in_sr;
+    if (P.tw_full_out) {   // table generation: twiddle of this element, in the input layout
+      uint64_t tq = P.tw_sel == 0 ? q0 : (P.tw_sel == 1 ? q1 : q2);
+      nt<F>::st(P.tw_full_out + 2 * off, nt<F>::tw(P.tab, (uint64_t)r * tq * P.tw_scale));
+      continue;
+    }
+    E x = nt<F>::ld(P.in + 2 * off);
     if (P.tw_sel >= 0 && r != 0) {
       uint64_t tq = P.tw_sel == 0 ? q0 : (P.tw_sel == 1 ? q1 : q2);
-      if (tq != 0) x = A::mul(x, nt<F>::tw(P.tab, (uint64_t)r * tq * P.tw_scale));
+      if (tq != 0) {
+        if (P.tw_full) x = A::mul(x, nt<F>::ld(P.tw_full + 2 * off));
+        else x = A::mul(x, nt<F>::tw(P.tab, (uint64_t)r * tq * P.tw_scale));
+      }
     }
     nt<F>::sts(lo, hi, r * V + v, x);
   }
+  if (P.tw_full_out) return;
   __syncthreads();
   // DIF rounds: radix 8 while possible, then 4 or 2
   int lblk = P.lr, rem = P.lr;

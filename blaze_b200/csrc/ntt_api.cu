@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -34,6 +35,7 @@ struct bz_ntt {
   NttTables tab{};
   bool tables_ready = false;
   std::vector<int> radices;
+  std::vector<uint4*> tw_full;   // per pass: twiddles in the pass' input layout (null for the first pass)
   cudaEvent_t ev[2] = {nullptr, nullptr};
   cudaEvent_t done = nullptr;
   bool launched = false;
@@ -48,6 +50,8 @@ static std::vector<int> plan_radices(int log_n) {
   for (int i = 0; i < npass; i++) r.push_back(i < extra ? base + 1 : base);
   return r;
 }
+
+static NttPassParams ntt_pass_params(bz_ntt* t, size_t p, uint64_t Ns);
 
 static int32_t ntt_alloc_slot(bz_ntt* t, int s) {
   for (int k = 0; k < 2; k++)
@@ -94,6 +98,7 @@ extern "C" int32_t bz_ntt_free(bz_ntt* t) {
   cudaStreamSynchronize(dc_stream(t->dc));
   for (auto& s : t->buf) for (auto& b : s) if (b) cudaFree(b);
   if (t->tab_mem) cudaFree(t->tab_mem);
+  for (auto p : t->tw_full) if (p) cudaFree(p);
   for (auto& e : t->ev) if (e) cudaEventDestroy(e);
   if (t->done) cudaEventDestroy(t->done);
   delete t;
@@ -127,6 +132,26 @@ extern "C" int32_t bz_ntt_initialize(bz_ntt* t) {
   t->tab.log_root = t->log_n;
   ntt_gen_tables(t->field, t->tab, t->log_n, t->inverse, dc_stream(t->dc));
   CUDA_TRY(BZ_ERR_UNKNOWN, cudaGetLastError());
+  // Precompute the inter-pass twiddles in each pass' input layout ("twiddles precomputed", one
+  // coalesced 32-B read per element instead of a two-level table product).  Costs n x 32 B per twiddled
+  // pass; skipped (two-level tables only) when BZ_NTT_FULL_TW=0 or the allocation fails.
+  const char* env = getenv("BZ_NTT_FULL_TW");
+  if (!(env && atoi(env) == 0) && t->log_n >= 10) {
+    t->tw_full.assign(t->radices.size(), nullptr);
+    uint64_t Ns = 1;
+    for (size_t p = 0; p < t->radices.size(); p++) {
+      if (Ns > 1) {
+        uint4* buf = nullptr;
+        if (cudaMalloc((void**)&buf, t->n * 32) != cudaSuccess) { cudaGetLastError(); break; }
+        NttPassParams P = ntt_pass_params(t, p, Ns);
+        P.tw_full_out = buf;
+        cudaError_t e = ntt_launch_pass(t->field, P, dc_stream(t->dc));
+        if (e != cudaSuccess) { cudaFree(buf); return bz_fail(BZ_ERR_UNKNOWN, "twiddle table pass failed: %s", cudaGetErrorString(e)); }
+        t->tw_full[p] = buf;
+      }
+      Ns <<= t->radices[p];
+    }
+  }
   t->tables_ready = true;
   return BZ_OK;
 }
@@ -146,44 +171,52 @@ extern "C" int32_t bz_ntt_set_data(bz_ntt* t, size_t buf_host, const uint8_t* da
   return BZ_OK;
 }
 
+// parameters of pass p (sub-transform size Ns) of the single-GPU transform
+static NttPassParams ntt_pass_params(bz_ntt* t, size_t p, uint64_t Ns) {
+  const uint64_t L = t->n;
+  const int lr = t->radices[p];
+  const uint64_t R = 1ull << lr;
+  NttPassParams P;
+  memset(&P, 0, sizeof(P));
+  P.lr = lr;
+  P.Q = L / R;
+  P.in_sr = L / R;
+  P.otw_rsel = -1;
+  P.tab = t->tab;
+  if (Ns == 1) {
+    P.Q0 = P.Q; P.Q1 = 1;
+    P.in_s0 = 1;
+    P.out_s0 = R; P.out_sr = 1;
+    P.tw_sel = -1;
+    P.store_k_fastest = 1;
+  } else {
+    P.Q0 = Ns; P.Q1 = L / (R * Ns);
+    P.in_s0 = 1; P.in_s1 = Ns;
+    P.out_s0 = 1; P.out_s1 = Ns * R; P.out_sr = Ns;
+    P.tw_sel = 0;
+    P.tw_scale = (1ull << t->log_n) / (Ns * R);
+    P.store_k_fastest = 0;
+  }
+  P.scale_ninv = (t->inverse && p + 1 == t->radices.size()) ? 1 : 0;
+  P.lq0 = 0; while ((1ull << P.lq0) < P.Q0) P.lq0++;
+  P.lq1 = 0; while ((1ull << P.lq1) < P.Q1) P.lq1++;
+  return P;
+}
+
 // enqueue all passes of one transform of slot s
 static int32_t ntt_enqueue(bz_ntt* t, int s) {
   cudaStream_t st = dc_stream(t->dc);
-  uint64_t L = t->n, Ns = 1;
+  uint64_t Ns = 1;
   cudaEventRecord(t->ev[0], st);
   for (size_t p = 0; p < t->radices.size(); p++) {
-    int lr = t->radices[p];
-    uint64_t R = 1ull << lr;
-    NttPassParams P;
-    memset(&P, 0, sizeof(P));
+    NttPassParams P = ntt_pass_params(t, p, Ns);
     P.in = t->buf[s][t->cur[s]];
     P.out = t->buf[s][t->cur[s] ^ 1];
-    P.lr = lr;
-    P.Q = L / R;
-    P.in_sr = L / R;
-    P.otw_rsel = -1;
-    P.tab = t->tab;
-    if (Ns == 1) {
-      P.Q0 = P.Q; P.Q1 = 1;
-      P.in_s0 = 1;
-      P.out_s0 = R; P.out_sr = 1;
-      P.tw_sel = -1;
-      P.store_k_fastest = 1;
-    } else {
-      P.Q0 = Ns; P.Q1 = L / (R * Ns);
-      P.in_s0 = 1; P.in_s1 = Ns;
-      P.out_s0 = 1; P.out_s1 = Ns * R; P.out_sr = Ns;
-      P.tw_sel = 0;
-      P.tw_scale = (1ull << t->log_n) / (Ns * R);
-      P.store_k_fastest = 0;
-    }
-    P.scale_ninv = (t->inverse && p + 1 == t->radices.size()) ? 1 : 0;
-    P.lq0 = 0; while ((1ull << P.lq0) < P.Q0) P.lq0++;
-    P.lq1 = 0; while ((1ull << P.lq1) < P.Q1) P.lq1++;
+    P.tw_full = p < t->tw_full.size() ? t->tw_full[p] : nullptr;
     cudaError_t e = ntt_launch_pass(t->field, P, st);
     if (e != cudaSuccess) return bz_fail(BZ_ERR_UNKNOWN, "NTT pass launch failed: %s", cudaGetErrorString(e));
     t->cur[s] ^= 1;
-    Ns *= R;
+    Ns <<= t->radices[p];
   }
   cudaEventRecord(t->ev[1], st);
   cudaEventRecord(t->done, st);

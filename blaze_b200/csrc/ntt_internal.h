@@ -37,6 +37,9 @@ struct NttPassParams {
   uint64_t out_s0, out_s1, out_s2, out_sr;
   int tw_sel;                       // input twiddle w^(r * q[tw_sel] * tw_scale); -1 = none
   uint64_t tw_scale;
+  const uint4* tw_full;             // optional: the same twiddles precomputed in the pass' INPUT layout (one per
+                                    // element, coalesced like the data) -- saves the two-level table product
+  uint4* tw_full_out;               // table-generation mode: write the twiddle of every element here and return
   // output twiddle w^((row * col mod 2^log_root) * otw_scale), row = q[otw_rsel] * otw_ra + k * otw_rb,
   // col = otw_base + q0 (the four-step twiddle between the column and the row transforms); otw_rsel < 0 = none
   int otw_rsel;

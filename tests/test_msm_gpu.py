@@ -264,3 +264,95 @@ def test_msm_large_closed_form(dclient, oracle, log_n):
             assert got == oracle.msm_pippenger("BLS12_381", pts, sc, n)
     finally:
         m.close()
+
+
+def test_config3_bn254_2p24_dma_mode(dclient, oracle):
+    """BASELINE.json configs[2]: BN254 MSM 2^24, DMA mode (points AND scalars streamed from host
+    memory with the call).  Checked against the closed form of the chain workload (full-size,
+    size-independent property) -- the full oracle Pippenger would take minutes."""
+    c = CURVE_BY_NAME["BN254"]
+    n = 1 << 24
+    from util import seed_points
+    p0, q = seed_points(c, 91)
+    gen = MSMClient.new(MSMInit(PointMemoryType.HBM, False, Curve.BN254), dclient)   # BN254 x HBM: todo!() in the reference
+    try:
+        gen.generate_chain_points(p0 + q, 0, n, 0, 0)
+        pts = np.frombuffer(gen.get_data_from_hbm(n * 64, 0, 0), dtype=np.uint8)
+    finally:
+        gen.close()
+    sc = random_scalars(c, n, seed=92)
+    got, _, plan = run_dma(dclient, Curve.BN254, pts, sc, n)
+    assert got == oracle.chain_expected("BN254", p0, q, sc, n), plan
+    # spot-check the generated points against the oracle's own chain
+    exp_pts, _, _ = chain_points(c, 64, seed=91)
+    assert bytes(pts[:64 * 64]) == bytes(exp_pts)
+
+
+def test_config5_bls12_377_hbm_closed_form(dclient, oracle):
+    """BASELINE.json configs[4] curve (BLS12-377), HBM-resident points, 2^20 per GPU shard."""
+    c = CURVE_BY_NAME["BLS12_377"]
+    n = 1 << 20
+    from util import seed_points
+    p0, q = seed_points(c, 93)
+    m = MSMClient.new(MSMInit(PointMemoryType.HBM, False, Curve.BLS377), dclient)
+    try:
+        first = 12345                      # a shard that does not start at index 0
+        m.generate_chain_points(p0 + q, first, n, 0x4000000, 0)
+        sc = random_scalars(c, n, seed=94)
+        params = MSMParams(n, (0x4000000, 0))
+        m.initialize(params)
+        m.start_process()
+        m.set_data(MSMInput(None, sc, params))
+        m.wait_result()
+        assert m.result().result == oracle.chain_expected("BLS12_377", p0, q, sc, n, index_base=first)
+    finally:
+        m.close()
+
+
+def test_msm_precompute_hbm_resident(dclient, oracle):
+    """integration_msm_hbm.rs `hbm_msm_bls12_381_precomp_test` shape: x8 bases loaded once into HBM
+    (mem_type DMA + an hbm address => HBM mode, msm_api.rs:75-95), then scalars-only tasks."""
+    c = CURVE_BY_NAME["BLS12_381"]
+    n = 2048 + 5
+    pts, _, _ = chain_points(c, n, seed=95)
+    bases8 = precompute_bases(c, pts, n, 8)
+    m = MSMClient.new(MSMInit(PointMemoryType.DMA, True, Curve.BLS381), dclient)
+    try:
+        addr = (0x8000000, 0x100)
+        params = MSMParams(n, addr)
+        m.load_data_to_hbm(bases8, *addr)
+        for it in range(2):
+            sc = random_scalars(c, n, seed=96 + it)
+            m.initialize(params)
+            m.start_process()
+            m.set_data(MSMInput(None, sc, params))
+            m.wait_result()
+            assert m.result().result == oracle.msm_pippenger("BLS12_381", pts, sc, n)
+    finally:
+        m.close()
+
+
+def test_msm_task_queue_two_in_flight(dclient, oracle):
+    """Two tasks queued back to back (the copy of the second overlaps the kernels of the first);
+    results pop in FIFO order with increasing labels (msm_api.rs:260-273)."""
+    c = CURVE_BY_NAME["BLS12_381"]
+    n = 1 << 14
+    pts, p0, q = chain_points(c, n, seed=97)
+    m = MSMClient.new(MSMInit(PointMemoryType.HBM, False, Curve.BLS381), dclient)
+    try:
+        params = MSMParams(n, (0, 0))
+        m.load_data_to_hbm(pts, 0, 0)
+        scs = [random_scalars(c, n, seed=98 + i) for i in range(3)]
+        for sc in scs:
+            m.initialize(params)
+            m.start_process()
+            m.set_data(MSMInput(None, sc, params))
+        labels = []
+        for sc in scs:
+            m.wait_result()
+            r = m.result()
+            labels.append(r.result_label)
+            assert r.result == oracle.chain_expected("BLS12_381", p0, q, sc, n)
+        assert labels == [labels[0], labels[0] + 1, labels[0] + 2]
+    finally:
+        m.close()
