@@ -77,6 +77,13 @@ BZ_DI uint64_t addc_cc64(uint64_t a, uint64_t b) {
 BZ_DI uint64_t addc64(uint64_t a, uint64_t b) {
   uint64_t r; asm volatile("addc.u64 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
 }
+// a + (CC << 32): consume the carry flag into the HIGH 32-bit half of a 64-bit word (one IADD3.X)
+BZ_DI uint64_t addc_hi32(uint64_t a) {
+  uint64_t r;
+  asm volatile("{\n\t.reg .u32 lo, hi;\n\tmov.b64 {lo, hi}, %1;\n\taddc.u32 hi, hi, 0;\n\tmov.b64 %0, {lo, hi};\n\t}"
+               : "=l"(r) : "l"(a));
+  return r;
+}
 #else
 // ---- host emulation (test vehicle) ----
 inline uint32_t& flag() { static thread_local uint32_t f = 0; return f; }
@@ -113,6 +120,7 @@ inline uint64_t add3_64(uint64_t a, uint64_t b, uint32_t cin, bool set) {
 inline uint64_t add_cc64(uint64_t a, uint64_t b) { return add3_64(a, b, 0, true); }
 inline uint64_t addc_cc64(uint64_t a, uint64_t b) { return add3_64(a, b, flag(), true); }
 inline uint64_t addc64(uint64_t a, uint64_t b) { return add3_64(a, b, flag(), false); }
+inline uint64_t addc_hi32(uint64_t a) { return a + ((uint64_t)flag() << 32); }
 #endif
 
 }  // namespace cc

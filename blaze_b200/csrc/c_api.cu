@@ -403,7 +403,7 @@ static int32_t make_plan(bz_msm* m, uint64_t M, int words_per_scalar) {
     if (ch >= 2 && (ch & (ch - 1)) == 0 && ch <= 1024) p.chunk = ch;
   }
   p.nchunks = (p.nvalues + p.chunk - 1) / p.chunk;
-  uint32_t nch1 = (p.nchunks + p.chunk - 1) / p.chunk;
+  uint32_t nch1 = (p.nchunks + 3) / 4;   // upper reduction levels use chunks of 4 (msm_curve.cuh)
 
   size_t xb = m->ops->xyzz_bytes;
   cudaError_t e = cudaSuccess;

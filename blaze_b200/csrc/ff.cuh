@@ -118,8 +118,7 @@ struct ff {
       Ev[0] = cc::add_cc64(Ev[0], cc::mad_wide(a[0], bi, h));
 #pragma unroll
       for (int k = 1; k < NW; k++) Ev[k] = cc::addc_cc64(Ev[k], cc::mul_wide(a[2 * k], bi));
-      uint64_t c = cc::addc64(0ull, 0ull);
-      Ov[NW - 1] += c << 32;
+      Ov[NW - 1] = cc::addc_hi32(Ov[NW - 1]);   // carry out of the even chain = bit 32 of the top odd word
     }
     uint32_t m = (uint32_t)Ev[0] * F::INV;
     Ov[0] = cc::add_cc64(Ov[0], cc::mul_wide(F::mod()[1], m));
@@ -129,8 +128,7 @@ struct ff {
     Ev[0] = cc::add_cc64(Ev[0], cc::mul_wide(F::mod()[0], m));
 #pragma unroll
     for (int k = 1; k < NW; k++) Ev[k] = cc::addc_cc64(Ev[k], cc::mul_wide(F::mod()[2 * k], m));
-    uint64_t c2 = cc::addc64(0ull, 0ull);
-    Ov[NW - 1] += c2 << 32;
+    Ov[NW - 1] = cc::addc_hi32(Ov[NW - 1]);
   }
 
   // r = a*b/R mod p
@@ -197,8 +195,7 @@ struct ff {
 #pragma unroll
       for (int k = 1; k < NW; k++)
         Ev[k] = cc::addc_cc64(Ev[k], k >= KE ? cc::mul_wide(sq_limb(a, d, I, 2 * k), bi) : 0ull);
-      uint64_t c = cc::addc64(0ull, 0ull);
-      Ov[NW - 1] += c << 32;
+      Ov[NW - 1] = cc::addc_hi32(Ov[NW - 1]);   // carry out of the even chain = bit 32 of the top odd word
     }
     uint32_t m = (uint32_t)Ev[0] * F::INV;
     Ov[0] = cc::add_cc64(Ov[0], cc::mul_wide(F::mod()[1], m));
@@ -208,8 +205,7 @@ struct ff {
     Ev[0] = cc::add_cc64(Ev[0], cc::mul_wide(F::mod()[0], m));
 #pragma unroll
     for (int k = 1; k < NW; k++) Ev[k] = cc::addc_cc64(Ev[k], cc::mul_wide(F::mod()[2 * k], m));
-    uint64_t c2 = cc::addc64(0ull, 0ull);
-    Ov[NW - 1] += c2 << 32;
+    Ov[NW - 1] = cc::addc_hi32(Ov[NW - 1]);
   }
   template <int I>
   BZ_HDI static void sqr_rows(uint64_t* Ev, uint64_t* Ov, const uint32_t* a, const uint32_t* d) {

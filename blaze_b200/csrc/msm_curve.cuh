@@ -430,23 +430,25 @@ struct CurveLaunch {
     }   // !batch_affine
     // multi-level running-sum reduction (see k_reduce_level); scratch: red_a = S / V of even levels, red_b = odd
     g_kernel_launches += 2;   // accumulate, finish
-    const uint32_t s = p.chunk;
-    int log_s = 0;
-    while ((1u << log_s) < s) log_s++;
+    // level 0 uses p.chunk entries per thread (throughput); the upper levels are tiny and latency-bound,
+    // so they use chunks of 4 (total chain length ~ s log_s n is shortest for small s)
     const XyzzM<C>* A = buckets;
     const XyzzM<C>* Vin = nullptr;
     uint32_t n = p.nvalues, a_stride = p.nb;
     int perm_bits = p.cbits;
     XyzzM<C>* scratch[2] = {(XyzzM<C>*)ws.red_a, (XyzzM<C>*)ws.red_b};
-    int level = 0;
+    int level = 0, shift = 0;
     const XyzzM<C>* top = nullptr;
     while (true) {
+      const uint32_t s = level == 0 ? p.chunk : 4;
+      int log_s = 0;
+      while ((1u << log_s) < s) log_s++;
       uint32_t nch = (n + s - 1) / s;
       XyzzM<C>* Sout = scratch[level & 1];
       XyzzM<C>* Vout = Sout + (size_t)p.W * nch;
       uint32_t nt = (uint32_t)p.W * nch;
-      k_reduce_level<C><<<(nt + 127) / 128, 128, 0, st>>>(A, Vin, n, a_stride, perm_bits, p.nfine, s, nch, p.W,
-                                                        level * log_s, Sout, Vout);
+      k_reduce_level<C><<<(nt + 127) / 128, 128, 0, st>>>(A, Vin, n, a_stride, perm_bits, p.nfine, s, nch, p.W, shift, Sout,
+                                                        Vout);
       g_kernel_launches += 1;
       top = Vout;
       if (nch == 1) break;
@@ -455,6 +457,7 @@ struct CurveLaunch {
       n = nch;
       a_stride = nch;
       perm_bits = -1;
+      shift += log_s;
       level++;
     }
     k_finish<C><<<1, 32, 0, st>>>(top, p.W, p.c, ws.result);
