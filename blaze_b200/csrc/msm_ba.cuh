@@ -85,6 +85,38 @@ struct ba {
     return lo;
   }
 
+  __device__ __forceinline__ static E load_x(const AffineM<C>* p) { return ld_fe(p->x); }
+  __device__ __forceinline__ static E load_y(const AffineM<C>* p, bool negate) {
+    E y = ld_fe(p->y);
+    return negate ? F::neg(y) : y;
+  }
+  // Forward-pass variant: where the two inputs of output slot p live (null src2 = no pair); returns like fetch.
+  __device__ __forceinline__ static int locate(const Round& R, uint32_t p, uint32_t g, const AffineM<C>*& s1, bool& n1,
+                                               const AffineM<C>*& s2, bool& n2) {
+    const uint32_t g0 = __ldg(R.goff + g), g1 = __ldg(R.goff + g + 1);
+    const uint32_t k0 = g1 - g0;
+    const uint32_t j = p - ((g0 >> (R.r + 1)) + g);
+    const uint32_t kr = (uint32_t)(((uint64_t)k0 + ((1ull << R.r) - 1)) >> R.r);
+    const uint32_t kr1 = (kr + 1) >> 1;
+    if (j >= kr1) return 0;
+    const bool pair = 2 * j + 1 < kr;
+    n1 = n2 = false;
+    if (R.r == 0) {
+      uint32_t e = __ldg(R.sorted + g0 + 2 * j);
+      s1 = R.table + (e & 0x7fffffffu);
+      n1 = (e >> 31) != 0;
+      if (pair) {
+        e = __ldg(R.sorted + g0 + 2 * j + 1);
+        s2 = R.table + (e & 0x7fffffffu);
+        n2 = (e >> 31) != 0;
+      }
+    } else {
+      s1 = R.in + ((g0 >> R.r) + g) + 2 * j;
+      s2 = s1 + 1;
+    }
+    return pair ? 2 : 1;
+  }
+
   // What output slot p of bucket g computes: returns 0 = nothing (gap), 1 = copy of p1, 2 = p1 + p2.
   __device__ __forceinline__ static int fetch(const Round& R, uint32_t p, uint32_t g, Affine<C>& p1, Affine<C>& p2) {
     const uint32_t g0 = __ldg(R.goff + g), g1 = __ldg(R.goff + g + 1);
@@ -128,11 +160,20 @@ __global__ void __launch_bounds__(128) k_ba_forward(typename ba<C>::Round R, uin
       uint32_t p = base + i * 32;
       if (p >= R.nslots) break;
       while (g + 1 < R.ngoff && B::slot0(R, g + 1, R.r + 1) <= p) g++;
-      Affine<C> p1, p2;
-      int what = B::fetch(R, p, g, p1, p2);
+      const AffineM<C>*s1 = nullptr, *s2 = nullptr;
+      bool n1, n2;
+      int what = B::locate(R, p, g, s1, n1, s2, n2);
       if (what == 2) {
-        typename B::E den;
-        ec<C>::ba_classify(p1, p2, den);
+        // the x coordinates decide the generic case (both non-zero and different => chord, den = x2 - x1,
+        // exactly what ba_classify returns); only the rare rest needs the y coordinates as well
+        typename B::E x1 = B::load_x(s1), x2 = B::load_x(s2);
+        typename B::E den = F::sub(x2, x1);
+        if (F::is_zero(x1) || F::is_zero(x2) || F::is_zero(den)) {
+          Affine<C> p1, p2;
+          p1.x = x1; p1.y = B::load_y(s1, n1);
+          p2.x = x2; p2.y = B::load_y(s2, n2);
+          ec<C>::ba_classify(p1, p2, den);
+        }
         run = F::mul(run, den);
       }
       B::st_fe(pref + (size_t)p * B::N, run);
