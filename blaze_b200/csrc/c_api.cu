@@ -426,7 +426,7 @@ static int32_t make_plan(bz_msm* m, uint64_t M, int words_per_scalar) {
   }
   A(&m->ws.wbase, (size_t)(p.W + 1) * 4);
   if (p.batch_affine) {
-    const size_t fb = (size_t)m->ops->fq_bytes, ab = m->ops->affine_bytes;
+    const size_t fb = (size_t)m->ops->fq_bytes, ab = m->ops->affine_list_bytes;
     const uint64_t ng = (uint64_t)p.W * p.nb;
     const uint64_t S1 = (total >> 1) + ng, S2 = (total >> 2) + ng;
     const uint64_t n0 = ((S1 + 511) / 512) * 32 + 256, n1 = n0 / 256 + 2, n2 = n1 / 256 + 2, n3 = n2 / 256 + 2;

@@ -41,7 +41,7 @@ struct ba {
   static constexpr int N = Fq::N;
 
   struct Round {
-    const AffineM<C>* table;    // round 0 inputs: Montgomery table + sorted refs
+    const AffineT<C>* table;    // round 0 inputs: Montgomery table + sorted refs
     const uint32_t* sorted;
     const uint32_t* goff;       // bucket offsets of round 0 (ngoff + 1 entries)
     uint32_t ngoff;
@@ -85,14 +85,15 @@ struct ba {
     return lo;
   }
 
-  __device__ __forceinline__ static E load_x(const AffineM<C>* p) { return ld_fe(p->x); }
-  __device__ __forceinline__ static E load_y(const AffineM<C>* p, bool negate) {
-    E y = ld_fe(p->y);
+  // records are addressed by the pointer to their x[0] (table entries are padded, list entries packed)
+  __device__ __forceinline__ static E load_x(const uint32_t* rec) { return ld_fe(rec); }
+  __device__ __forceinline__ static E load_y(const uint32_t* rec, bool negate) {
+    E y = ld_fe(rec + N);
     return negate ? F::neg(y) : y;
   }
   // Forward-pass variant: where the two inputs of output slot p live (null src2 = no pair); returns like fetch.
-  __device__ __forceinline__ static int locate(const Round& R, uint32_t p, uint32_t g, const AffineM<C>*& s1, bool& n1,
-                                               const AffineM<C>*& s2, bool& n2) {
+  __device__ __forceinline__ static int locate(const Round& R, uint32_t p, uint32_t g, const uint32_t*& s1, bool& n1,
+                                               const uint32_t*& s2, bool& n2) {
     const uint32_t g0 = __ldg(R.goff + g), g1 = __ldg(R.goff + g + 1);
     const uint32_t k0 = g1 - g0;
     const uint32_t j = p - ((g0 >> (R.r + 1)) + g);
@@ -103,16 +104,16 @@ struct ba {
     n1 = n2 = false;
     if (R.r == 0) {
       uint32_t e = __ldg(R.sorted + g0 + 2 * j);
-      s1 = R.table + (e & 0x7fffffffu);
+      s1 = R.table[e & 0x7fffffffu].x;
       n1 = (e >> 31) != 0;
       if (pair) {
         e = __ldg(R.sorted + g0 + 2 * j + 1);
-        s2 = R.table + (e & 0x7fffffffu);
+        s2 = R.table[e & 0x7fffffffu].x;
         n2 = (e >> 31) != 0;
       }
     } else {
-      s1 = R.in + ((g0 >> R.r) + g) + 2 * j;
-      s2 = s1 + 1;
+      s1 = R.in[((g0 >> R.r) + g) + 2 * j].x;
+      s2 = s1 + 2 * N;
     }
     return pair ? 2 : 1;
   }
@@ -128,17 +129,17 @@ struct ba {
     const bool pair = 2 * j + 1 < kr;
     if (R.r == 0) {
       uint32_t e = __ldg(R.sorted + g0 + 2 * j);
-      p1 = D::load_affine(R.table + (e & 0x7fffffffu));
+      p1 = D::load_affine(R.table[e & 0x7fffffffu].x);
       if (e & 0x80000000u) p1.y = F::neg(p1.y);
       if (pair) {
         e = __ldg(R.sorted + g0 + 2 * j + 1);
-        p2 = D::load_affine(R.table + (e & 0x7fffffffu));
+        p2 = D::load_affine(R.table[e & 0x7fffffffu].x);
         if (e & 0x80000000u) p2.y = F::neg(p2.y);
       }
     } else {
       const AffineM<C>* src = R.in + ((g0 >> R.r) + g) + 2 * j;
-      p1 = D::load_affine(src);
-      if (pair) p2 = D::load_affine(src + 1);
+      p1 = D::load_affine(src->x);
+      if (pair) p2 = D::load_affine(src[1].x);
     }
     return pair ? 2 : 1;
   }
@@ -160,7 +161,7 @@ __global__ void __launch_bounds__(128) k_ba_forward(typename ba<C>::Round R, uin
       uint32_t p = base + i * 32;
       if (p >= R.nslots) break;
       while (g + 1 < R.ngoff && B::slot0(R, g + 1, R.r + 1) <= p) g++;
-      const AffineM<C>*s1 = nullptr, *s2 = nullptr;
+      const uint32_t *s1 = nullptr, *s2 = nullptr;
       bool n1, n2;
       int what = B::locate(R, p, g, s1, n1, s2, n2);
       if (what == 2) {
@@ -262,7 +263,7 @@ static __global__ void k_ba_maxk(const uint32_t* __restrict__ goff, uint32_t ngo
 
 // buckets[g] (XYZZ) = the single remaining point of bucket g after r* rounds
 template <class C>
-__global__ void __launch_bounds__(128) k_ba_gather(const AffineM<C>* __restrict__ table, const uint32_t* __restrict__ sorted,
+__global__ void __launch_bounds__(128) k_ba_gather(const AffineT<C>* __restrict__ table, const uint32_t* __restrict__ sorted,
                                                    const uint32_t* __restrict__ goff, uint32_t ngoff,
                                                    const AffineM<C>* __restrict__ list, int rstar,
                                                    XyzzM<C>* __restrict__ buckets) {
@@ -276,10 +277,10 @@ __global__ void __launch_bounds__(128) k_ba_gather(const AffineM<C>* __restrict_
     Affine<C> a;
     if (rstar == 0) {
       uint32_t e = sorted[g0];
-      a = D::load_affine(table + (e & 0x7fffffffu));
+      a = D::load_affine(table[e & 0x7fffffffu].x);
       if (e & 0x80000000u) a.y = ff<typename C::Fq>::neg(a.y);
     } else {
-      a = D::load_affine(list + ((g0 >> rstar) + g));
+      a = D::load_affine(list[(g0 >> rstar) + g].x);
     }
     r = G::from_affine(a);
   }
@@ -308,7 +309,7 @@ static void ba_bucket_phase(const MsmPlan& p, const MsmWorkspace& ws, const void
   if (ws.ev_acc0) cudaEventRecord(ws.ev_acc0, st);
   for (int r = 0; r < rstar; r++) {
     typename B::Round R;
-    R.table = (const AffineM<C>*)table;
+    R.table = (const AffineT<C>*)table;
     R.sorted = ws.sorted;
     R.goff = ws.goff;
     R.ngoff = ngoff;
@@ -343,7 +344,7 @@ static void ba_bucket_phase(const MsmPlan& p, const MsmWorkspace& ws, const void
     g_kernel_launches += 3 + 2 * levels;
   }
   if (ws.ev_acc1) cudaEventRecord(ws.ev_acc1, st);
-  k_ba_gather<C><<<(ngoff + 127) / 128, 128, 0, st>>>((const AffineM<C>*)table, ws.sorted, ws.goff, ngoff, buf[rstar & 1], rstar,
+  k_ba_gather<C><<<(ngoff + 127) / 128, 128, 0, st>>>((const AffineT<C>*)table, ws.sorted, ws.goff, ngoff, buf[rstar & 1], rstar,
                                                     buckets);
   g_kernel_launches += 1;
 }

@@ -21,7 +21,14 @@
 namespace bz {
 
 template <class C>
-struct alignas(16) AffineM {
+struct alignas(16) AffineM {   // packed affine point (lists that are read sequentially)
+  uint32_t x[C::Fq::N], y[C::Fq::N];
+};
+// Entry of the resident Montgomery point table, which is only ever GATHERED: 96-byte records are padded to
+// 128 B so that one gather touches exactly one 128-byte DRAM line (unpadded they straddle two lines half
+// of the time: measured 197 B of DRAM traffic per 96-B record, profiles/r1_traffic.json).
+template <class C>
+struct alignas((sizeof(uint32_t) * 2 * C::Fq::N == 96) ? 128 : 16) AffineT {
   uint32_t x[C::Fq::N], y[C::Fq::N];
 };
 template <class C>
@@ -36,9 +43,10 @@ struct dev {
   typedef ff<Fq> F;
   typedef ec<C> G;
 
-  __device__ __forceinline__ static Affine<C> load_affine(const AffineM<C>* p) {
+  // rec points at x[0] of an AffineM / AffineT record (x then y, contiguous)
+  __device__ __forceinline__ static Affine<C> load_affine(const uint32_t* rec) {
     Affine<C> a;
-    const uint4* q = reinterpret_cast<const uint4*>(p);
+    const uint4* q = reinterpret_cast<const uint4*>(rec);
 #pragma unroll
     for (int k = 0; k < N / 4; k++) {
       uint4 v = __ldg(q + k);
@@ -106,7 +114,7 @@ struct dev {
 
 // ---------------------------------------------------------------------------------------------
 template <class C>
-__global__ void __launch_bounds__(128) k_points_to_mont(const uint8_t* __restrict__ raw, AffineM<C>* __restrict__ table,
+__global__ void __launch_bounds__(128) k_points_to_mont(const uint8_t* __restrict__ raw, AffineT<C>* __restrict__ table,
                                                         uint64_t n) {
   typedef dev<C> D;
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -124,7 +132,7 @@ __global__ void __launch_bounds__(128) k_points_to_mont(const uint8_t* __restric
 #endif
 template <class C>
 __global__ void __launch_bounds__(128, BZ_ACC_MINBLOCKS)
-k_accumulate(const AffineM<C>* __restrict__ table, const uint32_t* __restrict__ sorted,
+k_accumulate(const AffineT<C>* __restrict__ table, const uint32_t* __restrict__ sorted,
              const uint32_t* __restrict__ goff, XyzzM<C>* __restrict__ buckets, uint32_t* __restrict__ part_id,
              XyzzM<C>* __restrict__ part_pt, uint64_t nseg, uint32_t L, uint32_t nb, uint32_t ngoff) {
   typedef dev<C> D;
@@ -154,14 +162,14 @@ k_accumulate(const AffineM<C>* __restrict__ table, const uint32_t* __restrict__ 
   // software pipeline: the point of entry pos+1 and the index of entry pos+2 are in flight while the
   // mixed add of entry pos runs (a gather miss costs ~1 us, an add ~8 us)
   uint32_t ent_n = __ldg(sorted + s);
-  Affine<C> a_n = D::load_affine(table + (ent_n & 0x7fffffffu));
+  Affine<C> a_n = D::load_affine(table[ent_n & 0x7fffffffu].x);
   uint32_t ent_n2 = s + 1 < e ? __ldg(sorted + s + 1) : 0;
 
   for (uint32_t pos = s; pos < e; pos++) {
     const uint32_t ent = ent_n;
     Affine<C> a = a_n;
     ent_n = ent_n2;
-    if (pos + 1 < e) a_n = D::load_affine(table + (ent_n & 0x7fffffffu));
+    if (pos + 1 < e) a_n = D::load_affine(table[ent_n & 0x7fffffffu].x);
     if (pos + 2 < e) ent_n2 = __ldg(sorted + pos + 2);
     if (pos == bend) {
       // bucket g is finished (bend <= e here)
@@ -389,7 +397,7 @@ template <class C>
 struct CurveLaunch {
   static void points_to_mont(const uint8_t* raw, void* table, uint64_t n, cudaStream_t st) {
     if (!n) return;
-    k_points_to_mont<C><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(raw, (AffineM<C>*)table, n);
+    k_points_to_mont<C><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(raw, (AffineT<C>*)table, n);
     g_kernel_launches += 1;
   }
   static void bucket_phase(const MsmPlan& p, const MsmWorkspace& ws, const void* table, cudaStream_t st) {
@@ -401,7 +409,7 @@ struct CurveLaunch {
     } else {
     if (ws.ev_acc0) cudaEventRecord(ws.ev_acc0, st);
     k_accumulate<C><<<(unsigned)((p.nseg + 127) / 128), 128, 0, st>>>(
-        (const AffineM<C>*)table, ws.sorted, ws.goff, buckets, ws.part_id, (XyzzM<C>*)ws.part_pt, p.nseg, p.seg_len,
+        (const AffineT<C>*)table, ws.sorted, ws.goff, buckets, ws.part_id, (XyzzM<C>*)ws.part_pt, p.nseg, p.seg_len,
         p.nb, ngoff);
     if (ws.ev_acc1) cudaEventRecord(ws.ev_acc1, st);
     {
@@ -477,6 +485,7 @@ struct CurveLaunch {
                                C::FQ_BYTES,
                                C::SCALAR_BITS,
                                fr_mod_host(),
+                               sizeof(AffineT<C>),
                                sizeof(AffineM<C>),
                                sizeof(XyzzM<C>),
                                &points_to_mont,

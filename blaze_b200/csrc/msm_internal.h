@@ -89,7 +89,8 @@ struct CurveOps {
   int fq_bytes;          // 48 / 32
   int scalar_bits;       // 253 / 254 / 255
   const uint32_t* fr_mod;   // 8 limbs, host copy
-  size_t affine_bytes;   // Montgomery affine table entry
+  size_t affine_bytes;   // Montgomery affine TABLE entry (padded for single-line gathers)
+  size_t affine_list_bytes;   // packed affine point (batched-affine lists)
   size_t xyzz_bytes;
   void (*points_to_mont)(const uint8_t* raw, void* table, uint64_t n, cudaStream_t st);
   void (*bucket_phase)(const MsmPlan& p, const MsmWorkspace& ws, const void* table, cudaStream_t st);
