@@ -371,6 +371,8 @@ static int32_t make_plan(bz_msm* m, uint64_t M, int words_per_scalar) {
   if (!best_c) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "no feasible window size for %llu elements", (unsigned long long)M);
   p.batch_affine = 0;
   if (const char* e = getenv("BZ_MSM_BA")) p.batch_affine = atoi(e) ? 1 : 0;
+  p.tma_stage = 0;
+  if (const char* e = getenv("BZ_MSM_TMA")) p.tma_stage = atoi(e) ? 1 : 0;
   p.c = best_c;
   p.W = plan_windows(smax, sbits, p.c, p.dc);
   p.nvalues = (1u << (p.c - 1)) + 1;

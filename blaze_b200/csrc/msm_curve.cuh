@@ -199,6 +199,159 @@ k_accumulate(const AffineT<C>* __restrict__ table, const uint32_t* __restrict__ 
   part_id[2 * t + 1] = id1;
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_accumulate with the gathered points STAGED THROUGH SHARED MEMORY by the bulk-copy engine:
+// every lane issues `cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes` (SASS: UBLKCP) for
+// the point of its NEXT sorted entry into a per-warp two-stage ring and the warp's mbarrier of that
+// stage collects the 32 arrivals + transferred bytes; the mixed add of the current entry runs meanwhile.
+// Compared with the register-prefetch version above this frees the 24 registers of the in-flight point.
+// Ring slot stride is 112 B (7 x 16): 8 consecutive lanes reading 16-byte pieces hit 8 distinct banks.
+#define BZ_ACC_RING_STRIDE 112
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <class C>
+__global__ void __launch_bounds__(128, BZ_ACC_MINBLOCKS)
+k_accumulate_tma(const AffineT<C>* __restrict__ table, const uint32_t* __restrict__ sorted,
+                 const uint32_t* __restrict__ goff, XyzzM<C>* __restrict__ buckets, uint32_t* __restrict__ part_id,
+                 XyzzM<C>* __restrict__ part_pt, uint64_t nseg, uint32_t L, uint32_t nb, uint32_t ngoff) {
+  typedef dev<C> D;
+  typedef ec<C> G;
+  constexpr int N = C::Fq::N;
+  constexpr uint32_t PT_BYTES = 2 * N * 4;
+  extern __shared__ __align__(16) uint8_t ring_raw[];
+  // layout per warp: [2 stages][32 lanes][112 B], then (after all rings) [4 warps][2] mbarriers
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = blockDim.x >> 5;
+  uint8_t* ring = ring_raw + (size_t)warp * 2 * 32 * BZ_ACC_RING_STRIDE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring_raw + (size_t)nwarps * 2 * 32 * BZ_ACC_RING_STRIDE) + 2 * warp;
+  const uint32_t bar0 = smem_u32(bars), bar1 = bar0 + 8;
+  if (lane == 0) { mbar_init(bar0, 32); mbar_init(bar1, 32); }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t total = __ldg(goff + ngoff);
+  const uint64_t s64 = t * L;
+  const bool active = t < nseg && s64 < total;
+  const uint32_t s = active ? (uint32_t)s64 : 0;
+  const uint32_t e = active ? (uint32_t)(s64 + L < total ? s64 + L : total) : 0;
+  uint32_t g = 0, bstart = 0, bend = 0;
+  bool skip = true;
+  if (active) {
+    uint32_t lo = 0, hi = ngoff;
+    while (hi - lo > 1) {
+      uint32_t mid = lo + ((hi - lo) >> 1);
+      if (__ldg(goff + mid) <= s) lo = mid; else hi = mid;
+    }
+    g = lo;
+    bstart = __ldg(goff + g);
+    bend = __ldg(goff + g + 1);
+    skip = (g % nb) == 0;
+  }
+  uint32_t id0 = 0xffffffffu, id1 = 0xffffffffu;
+  XYZZ<C> acc = G::infinity();
+
+  // stage 0 <- entry s; index of entry s+1 in flight
+  uint32_t ent_n = active ? __ldg(sorted + s) : 0;
+  uint32_t ent_n2 = (active && s + 1 < e) ? __ldg(sorted + s + 1) : 0;
+  {
+    const uint32_t dst = smem_u32(ring + (size_t)lane * BZ_ACC_RING_STRIDE);
+    if (active) {
+      mbar_arrive_expect_tx(bar0, PT_BYTES);
+      bulk_g2s(dst, table[ent_n & 0x7fffffffu].x, PT_BYTES, bar0);
+    } else {
+      mbar_arrive(bar0);
+    }
+  }
+  // every lane of the warp runs the same number of iterations (the mbarriers count 32 arrivals)
+  for (uint32_t it = 0; it < L; it++) {
+    const uint32_t pos = s + it;
+    const bool have = active && pos < e;
+    const uint32_t ent = ent_n;
+    ent_n = ent_n2;
+    // refill the other stage with the point of entry pos+1 (its previous contents were consumed at it-1)
+    {
+      const uint32_t stage = (it + 1) & 1;
+      const uint32_t bar = stage ? bar1 : bar0;
+      if (it + 1 < L) {
+        if (active && pos + 1 < e) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          const uint32_t dst = smem_u32(ring + ((size_t)stage * 32 + lane) * BZ_ACC_RING_STRIDE);
+          mbar_arrive_expect_tx(bar, PT_BYTES);
+          bulk_g2s(dst, table[ent_n & 0x7fffffffu].x, PT_BYTES, bar);
+        } else {
+          mbar_arrive(bar);
+        }
+      }
+    }
+    if (active && pos + 2 < e) ent_n2 = __ldg(sorted + pos + 2);
+    // wait for this iteration's stage (k-th use of a stage completes phase k)
+    {
+      const uint32_t stage = it & 1;
+      const uint32_t bar = stage ? bar1 : bar0;
+      const uint32_t parity = (it >> 1) & 1;
+      while (!mbar_try_wait(bar, parity)) {}
+    }
+    if (!have) continue;
+    if (pos == bend) {
+      if (!skip) {
+        if (bstart >= s) D::store_xyzz(buckets + g, acc);
+        else { id0 = g; D::store_xyzz(part_pt + 2 * t, acc); }
+      }
+      do {
+        g++;
+        bstart = bend;
+        bend = __ldg(goff + g + 1);
+      } while (bend == pos);
+      skip = (g % nb) == 0;
+      acc = G::infinity();
+    }
+    if (!skip) {
+      const uint4* q = reinterpret_cast<const uint4*>(ring + ((size_t)(it & 1) * 32 + lane) * BZ_ACC_RING_STRIDE);
+      Affine<C> a;
+#pragma unroll
+      for (int k = 0; k < N / 4; k++) {
+        uint4 v = q[k];
+        a.x.v[4 * k] = v.x; a.x.v[4 * k + 1] = v.y; a.x.v[4 * k + 2] = v.z; a.x.v[4 * k + 3] = v.w;
+      }
+#pragma unroll
+      for (int k = 0; k < N / 4; k++) {
+        uint4 v = q[N / 4 + k];
+        a.y.v[4 * k] = v.x; a.y.v[4 * k + 1] = v.y; a.y.v[4 * k + 2] = v.z; a.y.v[4 * k + 3] = v.w;
+      }
+      if (ent & 0x80000000u) a.y = ff<typename C::Fq>::neg(a.y);
+      G::madd(acc, a);
+    }
+  }
+  if (t >= nseg) return;
+  if (active && !skip) {
+    if (bstart >= s && bend <= e) D::store_xyzz(buckets + g, acc);
+    else if (bstart < s) { id0 = g; D::store_xyzz(part_pt + 2 * t, acc); }
+    else { id1 = g; D::store_xyzz(part_pt + 2 * t + 1, acc); }
+  }
+  part_id[2 * t] = id0;
+  part_id[2 * t + 1] = id1;
+}
+
 // Fold the partial sums of buckets that straddle segment boundaries -- as a tree, so that one
 // bucket holding millions of entries (all scalars equal, or the reference's tiled test vectors) does
 // not serialise on one thread.  Level k: a thread owns `group` consecutive child units (segments at
@@ -408,9 +561,16 @@ struct CurveLaunch {
       ba_bucket_phase_fwd<C>(p, ws, table, st);
     } else {
     if (ws.ev_acc0) cudaEventRecord(ws.ev_acc0, st);
-    k_accumulate<C><<<(unsigned)((p.nseg + 127) / 128), 128, 0, st>>>(
-        (const AffineT<C>*)table, ws.sorted, ws.goff, buckets, ws.part_id, (XyzzM<C>*)ws.part_pt, p.nseg, p.seg_len,
-        p.nb, ngoff);
+    if (p.tma_stage) {
+      const size_t smem = (size_t)4 * 2 * 32 * BZ_ACC_RING_STRIDE + 4 * 2 * sizeof(uint64_t);
+      k_accumulate_tma<C><<<(unsigned)((p.nseg + 127) / 128), 128, smem, st>>>(
+          (const AffineT<C>*)table, ws.sorted, ws.goff, buckets, ws.part_id, (XyzzM<C>*)ws.part_pt, p.nseg, p.seg_len,
+          p.nb, ngoff);
+    } else {
+      k_accumulate<C><<<(unsigned)((p.nseg + 127) / 128), 128, 0, st>>>(
+          (const AffineT<C>*)table, ws.sorted, ws.goff, buckets, ws.part_id, (XyzzM<C>*)ws.part_pt, p.nseg, p.seg_len,
+          p.nb, ngoff);
+    }
     if (ws.ev_acc1) cudaEventRecord(ws.ev_acc1, st);
     {
       // merge tree over the partial list (see k_merge_level)

@@ -45,6 +45,7 @@ struct MsmPlan {
   uint32_t tile, ntiles;   // level-1 tile size / count
   uint32_t seg_len;        // sorted entries per accumulate thread
   uint64_t nseg;           // number of accumulate segments = ceil(W*M / seg_len)
+  int tma_stage;           // 1: k_accumulate_tma (points staged through shared memory by cp.async.bulk), 0: register prefetch
   int batch_affine;        // 1: accumulate buckets by batched affine addition (msm_ba.cuh), 0: XYZZ sweep
   uint32_t chunk;          // entries per reduce thread at every level of the running-sum recursion (power of two)
   uint32_t nchunks;        // ceil(nb / chunk): level-0 chunk count
