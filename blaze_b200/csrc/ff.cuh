@@ -131,8 +131,29 @@ struct ff {
     Ov[NW - 1] = cc::addc_hi32(Ov[NW - 1]);
   }
 
-  // r = a*b/R mod p
+  // r = a*b/R mod p.  With BZ_NOINLINE_MUL the product and the square are real function calls (operands
+  // and result travel in registers, ~35 MOVs per call): the unrolled bodies are 400 / 330 instructions, so
+  // a mixed add with ten of them inlined is ~62 KB of code per loop iteration -- twice the SM's 32 KB
+  // instruction cache (ncu: no_instruction stalls) -- while the called form keeps the loop under 24 KB.
   BZ_HDI static E mul(const E& a, const E& b) {
+#if defined(BZ_NOINLINE_MUL) && defined(__CUDACC__)
+    return mul_call(a, b);
+#else
+    return mul_inline(a, b);
+#endif
+  }
+  BZ_HDI static E sqr(const E& a) {
+#if defined(BZ_NOINLINE_MUL) && defined(__CUDACC__)
+    return sqr_call(a);
+#else
+    return sqr_inline(a);
+#endif
+  }
+#ifdef __CUDACC__
+  static __device__ __noinline__ E mul_call(const E a, const E b) { return mul_inline(a, b); }
+  static __device__ __noinline__ E sqr_call(const E a) { return sqr_inline(a); }
+#endif
+  BZ_HDI static E mul_inline(const E& a, const E& b) {
     constexpr int NW = N / 2;
     uint64_t Ev[NW], Ov[NW];
 #pragma unroll
@@ -215,9 +236,9 @@ struct ff {
       sqr_rows<I + 2>(Ev, Ov, a, d);
     }
   }
-  BZ_HDI static E sqr(const E& a) {
+  BZ_HDI static E sqr_inline(const E& a) {
     if constexpr (F::BITS + 2 > 32 * N) {
-      return mul(a, a);
+      return mul_inline(a, a);
     } else {
       return sqr_dedicated(a);
     }
