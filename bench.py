@@ -396,7 +396,9 @@ def main():
         tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("k_accumulate_dram_bytes_per_launch")
+                tj = json.load(open(tp))
+                # the ncu capture is of the 2^26 / 13-window launch; other shard sizes scale with the algorithmic bytes
+                traffic = tj.get("k_accumulate_dram_bytes_per_launch") * alg_bytes / tj.get("algorithmic_bytes_per_launch")
             except Exception:
                 traffic = None
         line = {
