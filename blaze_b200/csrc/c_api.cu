@@ -287,6 +287,15 @@ struct bz_msm {
   void* table = nullptr;
   uint64_t table_cap = 0, table_n = 0, table_addr = ~0ull, table_epoch = 0;
   bool table_from_arena = false;
+  // window-merged table (SURVEY 8(a) "HBM-resident precomputed points"): entry w*n + i = 2^(c w) * P_i.  Built on
+  // the second MSM over an unchanged resident point set (precomp_mode 1), immediately (2) or never (0).
+  void* wtable = nullptr;
+  size_t wtable_bytes = 0;
+  uint64_t wtable_n = 0, wtable_addr = ~0ull, wtable_epoch = 0;
+  int wtable_c = 0, wtable_levels = 0;
+  int precomp_mode = 1;
+  bool precomp_failed = false;   // allocation failed for this point set: stay on the plain table
+  uint64_t table_uses = 0;       // MSMs launched on the current arena table
   uint8_t* dma_points = nullptr;
   size_t dma_points_cap = 0;
   // scalar ingest: two staging buffers filled on a dedicated copy stream, so the H2D of task k+1
@@ -306,6 +315,14 @@ struct bz_msm {
   std::mutex mu;
 };
 
+static void wtable_free(bz_msm* m) {
+  if (m->wtable) cudaFree(m->wtable);
+  m->wtable = nullptr;
+  m->wtable_bytes = 0;
+  m->wtable_n = 0;
+  m->wtable_c = m->wtable_levels = 0;
+}
+
 static void ws_free(bz_msm* m) {
   for (void* p : m->ws_allocs) cudaFree(p);
   m->ws_allocs.clear();
@@ -323,11 +340,26 @@ static cudaError_t ws_alloc(bz_msm* m, T** p, size_t bytes) {
 
 static int ilog2_floor(uint64_t v) { int l = 0; while (v >>= 1) l++; return l; }
 
-static int32_t make_plan(bz_msm* m, uint64_t M, int words_per_scalar) {
-  if (m->have_plan && m->plan.M == M && m->plan.words_per_scalar == words_per_scalar &&
+static size_t ws_bytes_estimate(const bz_msm* m, uint64_t total, int c, int W) {
+  const size_t xb = m->ops->xyzz_bytes;
+  const uint64_t nseg = total / 256 + 1;
+  return (size_t)(total * 16 + (uint64_t)W * ((1ull << (c - 1)) + (1ull << 13)) * xb * 9 / 8 + nseg * 2 * (xb + 4) * 33 / 32 + (64ull << 20));
+}
+
+static int32_t make_plan(bz_msm* m, uint64_t M, int words_per_scalar, bool merged) {
+  if (m->have_plan && m->plan.M == M && m->plan.words_per_scalar == words_per_scalar && (m->plan.merged != 0) == merged &&
       (m->forced_c == 0 || m->forced_c == m->plan.c))
     return BZ_OK;
   ws_free(m);
+  size_t mem_free = 0, mem_total = 0;
+  if (merged) {
+    cudaMemGetInfo(&mem_free, &mem_total);
+    mem_free += m->wtable_bytes;   // an existing merged table is reused or replaced
+    double reserve_gb = 20.0;      // left for the caller's other clients (e.g. the 16 GiB of NTT slots at 2^27)
+    if (const char* e = getenv("BZ_MSM_PRECOMP_RESERVE_GB")) reserve_gb = atof(e);
+    size_t reserve = (size_t)(std::min(reserve_gb * 1073741824.0, (double)mem_total * 0.5));
+    mem_free = mem_free > reserve ? mem_free - reserve : 0;
+  }
   MsmPlan p{};
   p.M = M;
   p.words_per_scalar = words_per_scalar;
@@ -352,11 +384,19 @@ static int32_t make_plan(bz_msm* m, uint64_t M, int words_per_scalar) {
   int env_c = 0;
   if (const char* e = getenv("BZ_MSM_C")) env_c = atoi(e);
   int force = m->forced_c ? m->forced_c : env_c;
-  for (int c = 4; c <= 23; c++) {
+  for (int c = 4; c <= (merged ? 26 : 23); c++) {
     if (force && c != force) continue;
     DigitConst dcx{};
     int W = plan_windows(smax, sbits, c, dcx);
     if ((uint64_t)W * M >= (1ull << 32)) continue;
+    if (merged) {
+      // one bucket set: the reduction is paid once, the table costs W * M entries of HBM
+      if ((uint64_t)W * M >= (1ull << 31)) continue;   // entry index = w*M + i must leave bit 31 for the sign
+      if ((size_t)W * M * m->ops->affine_bytes + ws_bytes_estimate(m, (uint64_t)W * M, c, 1) > mem_free) continue;
+      double cost = (double)W * (double)M * 1.14 + 6.0 * (double)(1ull << (c - 1));
+      if (cost < best) { best = cost; best_c = c; }
+      continue;
+    }
     // measured on B200 (perf_probe, 2^24..2^26): per (scalar, window) the sort costs 0.14 of a mixed add
     // up to c = 20 and about doubles per two extra bits (more coarse bins -> more scattered writes);
     // the running-sum reduction costs about 6 mixed-add equivalents per bucket
@@ -368,19 +408,26 @@ static int32_t make_plan(bz_msm* m, uint64_t M, int words_per_scalar) {
     if (top_bits < 6 && M > (1u << 16)) cost *= 1.5;
     if (cost < best) { best = cost; best_c = c; }
   }
-  if (!best_c) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "no feasible window size for %llu elements", (unsigned long long)M);
+  if (!best_c) {
+    if (merged) return BZ_ERR_NO_RESULT;   // does not fit in HBM (caller falls back to the plain table); not an error
+    return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "no feasible window size for %llu elements", (unsigned long long)M);
+  }
   p.batch_affine = 0;
-  if (const char* e = getenv("BZ_MSM_BA")) p.batch_affine = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("BZ_MSM_BA")) p.batch_affine = (atoi(e) && !merged) ? 1 : 0;
   p.tma_stage = 0;
   if (const char* e = getenv("BZ_MSM_TMA")) p.tma_stage = atoi(e) ? 1 : 0;
   p.c = best_c;
-  p.W = plan_windows(smax, sbits, p.c, p.dc);
+  p.Wd = plan_windows(smax, sbits, p.c, p.dc);
+  p.merged = merged ? 1 : 0;
+  p.W = merged ? 1 : p.Wd;
+  p.Ms = merged ? (uint64_t)p.Wd * M : M;
+  const uint64_t Ms = p.Ms;
   p.nvalues = (1u << (p.c - 1)) + 1;
   // level-2 (fine) bits: a coarse bin should hold ~32K entries so that the CTA that sorts it owns a
   // small, quickly-filled output window (L2 merges its 4-byte scatter writes into full sectors)
   {
     int f = 1;
-    while (f < 10 && f < p.c - 1 && ((double)M / (double)(1ull << (p.c - 1 - (f + 1)))) <= 32768.0) f++;
+    while (f < 10 && f < p.c - 1 && ((double)Ms / (double)(1ull << (p.c - 1 - (f + 1)))) <= 32768.0) f++;
     p.fbits = std::max(1, std::min(f, p.c - 1));
     while (p.c - 1 - p.fbits > 13) p.fbits++;   // level-1 histogram (2^cbits counters) must fit shared memory
     if (const char* e = getenv("BZ_MSM_FBITS")) { int v = atoi(e); if (v >= 1 && v <= 12 && v < p.c && p.c - 1 - v <= 13) p.fbits = v; }
@@ -390,8 +437,9 @@ static int32_t make_plan(bz_msm* m, uint64_t M, int words_per_scalar) {
   p.nfine = (1u << p.fbits) + 1;
   p.nb = (uint32_t)p.ncoarse * p.nfine;
   p.tile = 65536;
-  p.ntiles = (uint32_t)((M + p.tile - 1) / p.tile);
-  uint64_t total = (uint64_t)p.W * M;
+  while ((Ms + p.tile - 1) / p.tile > 4096) p.tile <<= 1;   // k_colscan1 walks the tiles serially
+  p.ntiles = (uint32_t)((Ms + p.tile - 1) / p.tile);
+  uint64_t total = (uint64_t)p.W * Ms;
   // segment length: enough threads to fill the machine several times over, at most 256 entries each
   uint32_t L = 256;
   while (L > 16 && total / L < 148ull * 256 * 8) L >>= 1;
@@ -473,6 +521,7 @@ extern "C" int32_t bz_msm_new(bz_dclient* dc, int32_t curve, int32_t mem_type, i
   m->curve = curve;
   m->mem_type = mem_type;
   m->factor = is_precompute ? 8 : 1;   // PRECOMPUTE_FACTOR / PRECOMPUTE_FACTOR_BASE, msm_api.rs:39-40
+  if (const char* e = getenv("BZ_MSM_PRECOMP")) { int v = atoi(e); if (v >= 0 && v <= 2) m->precomp_mode = v; }
   for (auto& e : m->ev) cudaEventCreate(&e);
   cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking);
   for (int b = 0; b < 2; b++) {
@@ -499,6 +548,7 @@ extern "C" int32_t bz_msm_free(bz_msm* m) {
   for (auto& r : m->results) result_release(r);
   ws_free(m);
   if (m->table) cudaFree(m->table);
+  wtable_free(m);
   if (m->dma_points) cudaFree(m->dma_points);
   for (int b = 0; b < 2; b++) {
     if (m->scalars_dev[b]) cudaFree(m->scalars_dev[b]);
@@ -552,14 +602,58 @@ extern "C" int32_t bz_msm_initialize(bz_msm* m, uint32_t nof_elements, int32_t h
   return BZ_OK;
 }
 
+// make sure the window-merged table matches the current plan (c, Wd) and the resident point set
+static int32_t ensure_wtable(bz_msm* m, uint64_t n) {
+  const MsmPlan& p = m->plan;
+  if (m->wtable && m->wtable_n == n && m->wtable_c == p.c && m->wtable_levels == p.Wd && m->wtable_addr == m->table_addr &&
+      m->wtable_epoch == m->table_epoch)
+    return BZ_OK;
+  const size_t bytes = (size_t)p.Wd * n * m->ops->affine_bytes;
+  if (m->wtable_bytes < bytes) {
+    wtable_free(m);
+    if (cudaMalloc(&m->wtable, bytes) != cudaSuccess) {
+      cudaGetLastError();
+      m->wtable = nullptr;
+      return BZ_ERR_NO_RESULT;
+    }
+    m->wtable_bytes = bytes;
+  }
+  cudaStream_t st = m->dc->stream;
+  CUDA_TRY(BZ_ERR_WRITE, cudaMemcpyAsync(m->wtable, m->table, n * m->ops->affine_bytes, cudaMemcpyDeviceToDevice, st));
+  m->ops->build_wtable(m->wtable, n, p.Wd, p.c, st);
+  CUDA_TRY(BZ_ERR_UNKNOWN, cudaGetLastError());
+  m->wtable_n = n;
+  m->wtable_c = p.c;
+  m->wtable_levels = p.Wd;
+  m->wtable_addr = m->table_addr;
+  m->wtable_epoch = m->table_epoch;
+  return BZ_OK;
+}
+
 // enqueue the whole pipeline for one task on the client's stream
 static int32_t launch_task(bz_msm* m) {
   bz_dclient* dc = m->dc;
   const uint64_t M = m->data_M;
   const int wps = m->factor == 8 ? 1 : 8;
-  int32_t rc = make_plan(m, M, wps);
-  if (rc) return rc;
   cudaStream_t st = dc->stream;
+  // window-merged table: only for a resident (arena) point set with full-width scalars, and by default only once
+  // the same point set is used a second time (building it costs about as much as a dozen plain MSMs)
+  bool merged = false;
+  int32_t rc;
+  if (m->table_from_arena && wps == 8 && !m->precomp_failed &&
+      (m->precomp_mode == 2 || (m->precomp_mode == 1 && m->table_uses >= 1))) {
+    rc = make_plan(m, M, wps, true);
+    if (rc == BZ_OK) {
+      rc = ensure_wtable(m, M);
+      if (rc == BZ_OK) merged = true;
+    }
+    if (!merged) m->precomp_failed = true;
+  }
+  if (!merged) {
+    rc = make_plan(m, M, wps, false);
+    if (rc) return rc;
+  }
+  if (m->table_from_arena) m->table_uses++;
   MsmTaskResult r;
   r.label = m->next_label++;
   m->last_label = r.label;
@@ -578,7 +672,7 @@ static int32_t launch_task(bz_msm* m) {
     m->consumed_valid[m->stage_cur] = true;
   }
   cudaEventRecord(m->ev[1], st);
-  m->ops->bucket_phase(m->plan, m->ws, m->table, st);
+  m->ops->bucket_phase(m->plan, m->ws, merged ? m->wtable : m->table, st);
   cudaEventRecord(m->ev[4], st);
   m->timed = true;
   CUDA_TRY(BZ_ERR_UNKNOWN, cudaGetLastError());
@@ -626,6 +720,9 @@ static int32_t ensure_arena_table(bz_msm* m, uint64_t addr, uint64_t n_points) {
     int32_t rc = arena_reserve(dc, addr + bytes);   // unwritten HBM reads as zeros = identity padding
     if (rc) return rc;
   }
+  wtable_free(m);   // stale: derived from the previous point set
+  m->precomp_failed = false;
+  m->table_uses = 0;
   int32_t rc = build_table(m, dc->arena + addr, n_points);
   if (rc) return rc;
   m->table_from_arena = true;
@@ -812,15 +909,37 @@ extern "C" int32_t bz_msm_phase_times(bz_msm* m, float ms[4]) {
 }
 extern "C" int32_t bz_msm_set_window_bits(bz_msm* m, int32_t c) {
   if (!m) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null MSMClient");
-  if (c != 0 && (c < 4 || c > 23)) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "window bits must be 0 or in [4, 23]");
+  if (c != 0 && (c < 4 || c > 26)) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "window bits must be 0 or in [4, 26]");
   std::lock_guard<std::mutex> lk(m->mu);
   m->forced_c = c;
+  return BZ_OK;
+}
+extern "C" int32_t bz_msm_set_precompute(bz_msm* m, int32_t mode) {
+  if (!m) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null MSMClient");
+  if (mode < 0 || mode > 2) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "precompute mode must be 0 (never), 1 (on reuse) or 2 (always)");
+  std::lock_guard<std::mutex> lk(m->mu);
+  m->precomp_mode = mode;
+  m->precomp_failed = false;
+  return BZ_OK;
+}
+extern "C" int32_t bz_msm_plan_info_ex(bz_msm* m, uint32_t out[8]) {
+  if (!m || !out) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null argument");
+  memset(out, 0, 8 * sizeof(uint32_t));
+  if (!m->have_plan) return BZ_OK;
+  out[0] = m->plan.c;
+  out[1] = m->plan.Wd;        // digit windows = mixed adds per scalar
+  out[2] = m->plan.nvalues;
+  out[3] = m->plan.seg_len;
+  out[4] = m->plan.W;         // bucket sets (1 when the windows are merged)
+  out[5] = m->plan.merged;
+  out[6] = (uint32_t)(m->wtable_bytes >> 20);   // MiB held by the window-merged table
+  out[7] = m->plan.fbits;
   return BZ_OK;
 }
 extern "C" int32_t bz_msm_plan_info(bz_msm* m, uint32_t out[4]) {
   if (!m || !out) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null argument");
   out[0] = m->have_plan ? m->plan.c : 0;
-  out[1] = m->have_plan ? m->plan.W : 0;
+  out[1] = m->have_plan ? m->plan.Wd : 0;
   out[2] = m->have_plan ? m->plan.nvalues : 0;
   out[3] = m->have_plan ? m->plan.seg_len : 0;
   return BZ_OK;

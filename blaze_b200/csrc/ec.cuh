@@ -59,7 +59,7 @@ struct ec {
     E x2 = F::sqr(a.x);
     E M = F::add(F::dbl(x2), x2);
     r.X = F::sub(F::sqr(M), F::dbl(S));
-    r.Y = F::sub(F::mul(M, F::sub(S, r.X)), F::mul(W, a.y));
+    r.Y = F::mul_sub2(M, F::sub(S, r.X), W, a.y);
     r.ZZ = V;
     r.ZZZ = W;
     return r;   // y == 0 gives ZZ = 0 = infinity (2-torsion), consistent
@@ -75,7 +75,7 @@ struct ec {
     E x2 = F::sqr(p.X);
     E M = F::add(F::dbl(x2), x2);
     r.X = F::sub(F::sqr(M), F::dbl(S));
-    r.Y = F::sub(F::mul(M, F::sub(S, r.X)), F::mul(W, p.Y));
+    r.Y = F::mul_sub2(M, F::sub(S, r.X), W, p.Y);
     r.ZZ = F::mul(V, p.ZZ);
     r.ZZZ = F::mul(W, p.ZZZ);
     return r;
@@ -99,7 +99,7 @@ struct ec {
     E PPP = F::mul(Pd, PP);
     E Q = F::mul(acc.X, PP);
     E X3 = F::sub(F::sub(F::sqr(Rd), PPP), F::dbl(Q));
-    E Y3 = F::sub(F::mul(Rd, F::sub(Q, X3)), F::mul(acc.Y, PPP));
+    E Y3 = F::mul_sub2(Rd, F::sub(Q, X3), acc.Y, PPP);   // one reduction for both products
     acc.ZZ = F::mul(acc.ZZ, PP);
     acc.ZZZ = F::mul(acc.ZZZ, PPP);
     acc.X = X3;
@@ -125,7 +125,7 @@ struct ec {
     E PPP = F::mul(Pd, PP);
     E Q = F::mul(U1, PP);
     E X3 = F::sub(F::sub(F::sqr(Rd), PPP), F::dbl(Q));
-    E Y3 = F::sub(F::mul(Rd, F::sub(Q, X3)), F::mul(S1, PPP));
+    E Y3 = F::mul_sub2(Rd, F::sub(Q, X3), S1, PPP);
     acc.ZZ = F::mul(F::mul(acc.ZZ, b.ZZ), PP);
     acc.ZZZ = F::mul(F::mul(acc.ZZZ, b.ZZZ), PPP);
     acc.X = X3;

@@ -131,6 +131,90 @@ struct ff {
     Ov[NW - 1] = cc::addc_hi32(Ov[NW - 1]);
   }
 
+  // T += x * y: one more row pair on the E/O columns (the same schedule as the m * p row of step()); the
+  // carry out of the even chain lands in bit 32 of the top odd word
+  BZ_HDI static void add_row(uint64_t* Ev, uint64_t* Ov, const uint32_t* x, uint32_t y) {
+    constexpr int NW = N / 2;
+    Ov[0] = cc::add_cc64(Ov[0], cc::mul_wide(x[1], y));
+#pragma unroll
+    for (int k = 1; k < NW - 1; k++) Ov[k] = cc::addc_cc64(Ov[k], cc::mul_wide(x[2 * k + 1], y));
+    Ov[NW - 1] = cc::addc64(Ov[NW - 1], cc::mul_wide(x[N - 1], y));
+    Ev[0] = cc::add_cc64(Ev[0], cc::mul_wide(x[0], y));
+#pragma unroll
+    for (int k = 1; k < NW; k++) Ev[k] = cc::addc_cc64(Ev[k], cc::mul_wide(x[2 * k], y));
+    Ov[NW - 1] = cc::addc_hi32(Ov[NW - 1]);
+  }
+  // One step of the FUSED sum of two products a*b + c*d: both multiplier rows are accumulated before the
+  // single reduction row, so the pair costs 3 N^2 instead of 4 N^2 multiplier instructions.
+  // Bounds: after every division T < 3p + 1, before it T < 3p (1 + 2^32): fits the N+1 limb window when
+  // p < 2^(32N-2); the final value is < p (2p/R + 1) < 2p, so one conditional subtraction normalises it.
+  template <bool FIRST>
+  BZ_HDI static void step2(uint64_t* Ev, uint64_t* Ov, const uint32_t* a, uint32_t bi, const uint32_t* c, uint32_t di) {
+    static_assert(F::BITS + 2 <= 32 * N, "fused product sum needs two spare bits");
+    constexpr int NW = N / 2;
+    if (FIRST) {
+#pragma unroll
+      for (int k = 0; k < NW; k++) {
+        Ov[k] = cc::mul_wide(a[2 * k + 1], bi);
+        Ev[k] = cc::mul_wide(a[2 * k], bi);
+      }
+    } else {
+      uint64_t h = Ov[0] >> 32;
+      Ov[0] = cc::add_cc64(Ov[1], cc::mul_wide(a[1], bi));
+#pragma unroll
+      for (int k = 1; k < NW - 1; k++) Ov[k] = cc::addc_cc64(Ov[k + 1], cc::mul_wide(a[2 * k + 1], bi));
+      Ov[NW - 1] = cc::addc64(0ull, cc::mul_wide(a[N - 1], bi));
+      Ev[0] = cc::add_cc64(Ev[0], cc::mad_wide(a[0], bi, h));
+#pragma unroll
+      for (int k = 1; k < NW; k++) Ev[k] = cc::addc_cc64(Ev[k], cc::mul_wide(a[2 * k], bi));
+      Ov[NW - 1] = cc::addc_hi32(Ov[NW - 1]);
+    }
+    add_row(Ev, Ov, c, di);
+    uint32_t m = (uint32_t)Ev[0] * F::INV;
+    add_row(Ev, Ov, F::mod(), m);
+  }
+  // r = (a*b + c*d)/R mod p with ONE Montgomery reduction
+  BZ_HDI static E mul2_inline(const E& a, const E& b, const E& c, const E& d) {
+    constexpr int NW = N / 2;
+    uint64_t Ev[NW], Ov[NW];
+#pragma unroll
+    for (int i = 0; i < N; i += 2) {
+      if (i == 0) step2<true>(Ev, Ov, a.v, b.v[0], c.v, d.v[0]);
+      else        step2<false>(Ev, Ov, a.v, b.v[i], c.v, d.v[i]);
+      step2<false>(Ov, Ev, a.v, b.v[i + 1], c.v, d.v[i + 1]);
+    }
+    E r;
+    r.v[0] = cc::add_cc((uint32_t)Ev[0], (uint32_t)(Ov[0] >> 32));
+#pragma unroll
+    for (int j = 1; j < N - 1; j++) {
+      uint32_t e = (j & 1) ? (uint32_t)(Ev[j / 2] >> 32) : (uint32_t)Ev[j / 2];
+      uint32_t o = ((j + 1) & 1) ? (uint32_t)(Ov[(j + 1) / 2] >> 32) : (uint32_t)Ov[(j + 1) / 2];
+      r.v[j] = cc::addc_cc(e, o);
+    }
+    r.v[N - 1] = cc::addc((uint32_t)(Ev[NW - 1] >> 32), 0u);
+    final_sub(r.v);
+    return r;
+  }
+  // a*b + c*d and a*b - c*d (fields with two spare bits only; the others fall back to two products)
+  BZ_HDI static E mul2(const E& a, const E& b, const E& c, const E& d) {
+    if constexpr (F::BITS + 2 > 32 * N) {
+      return add(mul(a, b), mul(c, d));
+    } else {
+#if defined(BZ_NOINLINE_MUL) && defined(__CUDACC__)
+      return mul2_call(a, b, c, d);
+#else
+      return mul2_inline(a, b, c, d);
+#endif
+    }
+  }
+  BZ_HDI static E mul_sub2(const E& a, const E& b, const E& c, const E& d) {
+#ifdef BZ_NO_FUSED_MUL2
+    return sub(mul(a, b), mul(c, d));
+#else
+    return mul2(a, b, neg(c), d);
+#endif
+  }
+
   // r = a*b/R mod p.  With BZ_NOINLINE_MUL the product and the square are real function calls (operands
   // and result travel in registers, ~35 MOVs per call): the unrolled bodies are 400 / 330 instructions, so
   // a mixed add with ten of them inlined is ~62 KB of code per loop iteration -- twice the SM's 32 KB
@@ -152,6 +236,7 @@ struct ff {
 #ifdef __CUDACC__
   static __device__ __noinline__ E mul_call(const E a, const E b) { return mul_inline(a, b); }
   static __device__ __noinline__ E sqr_call(const E a) { return sqr_inline(a); }
+  static __device__ __noinline__ E mul2_call(const E a, const E b, const E c, const E d) { return mul2_inline(a, b, c, d); }
 #endif
   BZ_HDI static E mul_inline(const E& a, const E& b) {
     constexpr int NW = N / 2;

@@ -126,6 +126,70 @@ __global__ void __launch_bounds__(128) k_points_to_mont(const uint8_t* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
+// Window-merged table ("precomputed points resident in HBM", the HBM-mode path): level w holds
+// 2^(c w) * P_i, so digit window w of scalar i can use table entry w*n + i and ALL windows share one
+// bucket set -- one running-sum reduction instead of W, which makes wider windows (fewer mixed adds per
+// scalar) affordable.  A level is made from the one below: c Jacobian doublings per point (a = 0:
+// dbl-2009-l, 2M + 5S), then back to affine with ONE field inversion per thread shared by K points
+// (Montgomery's trick).  Built once per resident point set, reused by every MSM on it.
+template <class C, int K>
+__global__ void __launch_bounds__(128) k_wtable_level(const AffineT<C>* __restrict__ prev, AffineT<C>* __restrict__ next,
+                                                      uint64_t n, int c) {
+  typedef dev<C> D;
+  typedef ff<typename C::Fq> F;
+  typedef Fe<typename C::Fq> E;
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t i0 = t * K;
+  if (i0 >= n) return;
+  E Xs[K], Ys[K], Zs[K], pre[K];   // local memory (indexed dynamically): this kernel runs once per point set
+  E run = F::one();
+#pragma unroll 1
+  for (int k = 0; k < K; k++) {
+    Zs[k] = F::zero();
+    pre[k] = run;
+    if (i0 + k >= n) continue;
+    Affine<C> a = D::load_affine(prev[i0 + k].x);
+    if (ec<C>::is_identity(a)) continue;
+    E X = a.x, Y = a.y, Z = F::one();
+#pragma unroll 1
+    for (int d = 0; d < c; d++) {
+      E A = F::sqr(X), B = F::sqr(Y), Cc = F::sqr(B);
+      E t0 = F::sub(F::sub(F::sqr(F::add(X, B)), A), Cc);
+      E Dd = F::dbl(t0);
+      E Ee = F::add(F::dbl(A), A);
+      E Ff = F::sqr(Ee);
+      E Z3 = F::dbl(F::mul(Y, Z));
+      X = F::sub(Ff, F::dbl(Dd));
+      E c8 = F::dbl(F::dbl(F::dbl(Cc)));
+      Y = F::sub(F::mul(Ee, F::sub(Dd, X)), c8);
+      Z = Z3;
+    }
+    if (F::is_zero(Z)) continue;   // 2-torsion input (possible on curves with even cofactor): identity from here on
+    Xs[k] = X; Ys[k] = Y; Zs[k] = Z;
+    run = F::mul(run, Z);
+  }
+  E inv = F::inv(run);
+#pragma unroll 1
+  for (int k = K - 1; k >= 0; k--) {
+    if (i0 + k >= n) continue;
+    uint32_t* ox = next[i0 + k].x;
+    uint32_t* oy = next[i0 + k].y;
+    if (F::is_zero(Zs[k])) {
+#pragma unroll
+      for (int j = 0; j < D::N; j++) { ox[j] = 0; oy[j] = 0; }
+      continue;
+    }
+    E zi = F::mul(inv, pre[k]);
+    inv = F::mul(inv, Zs[k]);
+    E zi2 = F::sqr(zi);
+    E x = F::mul(Xs[k], zi2);
+    E y = F::mul(Ys[k], F::mul(zi2, zi));
+#pragma unroll
+    for (int j = 0; j < D::N; j++) { ox[j] = x.v[j]; oy[j] = y.v[j]; }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // bucket accumulation (the dominant kernel)
 #ifndef BZ_ACC_MINBLOCKS
 #define BZ_ACC_MINBLOCKS 2
@@ -630,6 +694,15 @@ struct CurveLaunch {
     }
     k_finish<C><<<1, 32, 0, st>>>(top, p.W, p.c, ws.result);
   }
+  static void build_wtable(void* wtable, uint64_t n, int levels, int c, cudaStream_t st) {
+    constexpr int K = 16;
+    AffineT<C>* t = (AffineT<C>*)wtable;
+    const uint64_t threads = (n + K - 1) / K;
+    for (int w = 1; w < levels; w++) {
+      k_wtable_level<C, K><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(t + (uint64_t)(w - 1) * n, t + (uint64_t)w * n, n, c);
+      g_kernel_launches += 1;
+    }
+  }
   static void combine_results(const uint8_t* recs, int n, uint8_t* out, cudaStream_t st) {
     k_combine_results<C><<<1, 32, 0, st>>>(recs, n, out);
   }
@@ -650,6 +723,7 @@ struct CurveLaunch {
                                sizeof(XyzzM<C>),
                                &points_to_mont,
                                &bucket_phase,
+                               &build_wtable,
                                &combine_results,
                                &gen_chain_points,
                                &field_selftest};

@@ -31,7 +31,11 @@ struct MsmPlan {
   uint64_t M;              // number of (sub)scalars == number of table points used
   int words_per_scalar;    // 8: full 256-bit scalars; 1: 32-bit limbs against a x8 precomputed table
   int c;                   // window bits
-  int W;                   // number of windows
+  int W;                   // number of BUCKET windows (bucket sets): Wd, or 1 when the windows are merged
+  int Wd;                  // number of DIGIT windows per scalar (mixed adds per scalar)
+  int merged;              // 1: window-merged table -- digit window w of scalar i uses table entry w*M + i
+                           //    (= 2^(c w) P_i, precomputed and resident in HBM) and all windows share one bucket set
+  uint64_t Ms;             // sort entries per bucket window: M, or Wd*M when merged (dig[][] read as one flat list)
   // Bucket VALUES per window are 0 .. 2^(c-1) (nvalues of them; value 0 is never accumulated).  The
   // sort splits a value b into coarse = b & (ncoarse-1) (LOW bits: level 1) and fine = b >> cbits (level
   // 2), so skewed digit ranges -- small scalars, a short top window -- still spread over all coarse
@@ -53,7 +57,7 @@ struct MsmPlan {
 };
 
 struct MsmWorkspace {
-  uint32_t* dig;       // [W][M]
+  uint32_t* dig;       // [Wd][M]  (merged: one window of Wd*M entries)
   uint32_t* hmat;      // [W][ntiles][ncoarse]
   uint32_t* tot;       // [W][ncoarse]
   uint32_t* base1;     // [W][ncoarse+1]
@@ -95,6 +99,8 @@ struct CurveOps {
   size_t xyzz_bytes;
   void (*points_to_mont)(const uint8_t* raw, void* table, uint64_t n, cudaStream_t st);
   void (*bucket_phase)(const MsmPlan& p, const MsmWorkspace& ws, const void* table, cudaStream_t st);
+  // window-merged table: level w (entries [w*n, (w+1)*n)) = 2^c * level w-1; level 0 must already be in place
+  void (*build_wtable)(void* wtable, uint64_t n, int levels, int c, cudaStream_t st);
   // sum `n` canonical result records (Z||Y||X) into one canonical record (multi-GPU combine)
   void (*combine_results)(const uint8_t* recs, int n, uint8_t* out, cudaStream_t st);
   // test / bench helpers

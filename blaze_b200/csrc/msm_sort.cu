@@ -233,24 +233,25 @@ __global__ void __launch_bounds__(256) k_sort2(const uint2* __restrict__ l1, uin
 
 // ---------------------------------------------------------------------------------------------
 void launch_msm_sort(const MsmPlan& p, const MsmWorkspace& ws, const uint32_t* scalars_dev, cudaStream_t st) {
-  const uint64_t M = p.M;
+  const uint64_t M = p.M;     // scalars
+  const uint64_t Ms = p.Ms;   // entries per bucket window (merged: all Wd digit windows form ONE list, index = w*M + i)
   {
     unsigned blocks = (unsigned)((M + 255) / 256);
-    k_digits<<<blocks, 256, 0, st>>>(scalars_dev, p.words_per_scalar, M, p.W, p.c, p.dc, ws.dig, ws.err);
+    k_digits<<<blocks, 256, 0, st>>>(scalars_dev, p.words_per_scalar, M, p.Wd, p.c, p.dc, ws.dig, ws.err);
   }
   dim3 g1(p.ntiles, p.W);
   size_t sh1 = (size_t)p.ncoarse * sizeof(uint32_t);
-  k_hist1<<<g1, 512, sh1, st>>>(ws.dig, M, (uint32_t)p.ncoarse - 1, p.ncoarse, p.tile, p.ntiles, ws.hmat);
+  k_hist1<<<g1, 512, sh1, st>>>(ws.dig, Ms, (uint32_t)p.ncoarse - 1, p.ncoarse, p.tile, p.ntiles, ws.hmat);
   {
     int n = p.W * p.ncoarse;
     k_colscan1<<<(n + 255) / 256, 256, 0, st>>>(ws.hmat, p.ntiles, p.ncoarse, p.W, ws.tot);
     k_binscan1<<<p.W, 1024, 0, st>>>(ws.tot, p.ncoarse, ws.base1);
     k_wbase<<<1, 32, 0, st>>>(ws.base1, p.ncoarse, p.W, ws.wbase, ws.goff + (size_t)p.W * p.nb);
   }
-  k_scatter1<<<g1, 512, sh1, st>>>(ws.dig, M, (uint32_t)p.ncoarse - 1, p.ncoarse, p.tile, p.ntiles, ws.hmat, ws.base1, ws.l1);
+  k_scatter1<<<g1, 512, sh1, st>>>(ws.dig, Ms, (uint32_t)p.ncoarse - 1, p.ncoarse, p.tile, p.ntiles, ws.hmat, ws.base1, ws.l1);
   dim3 g2(p.ncoarse, p.W);
   size_t sh2 = ((size_t)p.nfine + 256) * sizeof(uint32_t);
-  k_sort2<<<g2, 256, sh2, st>>>(ws.l1, M, p.cbits, p.ncoarse, p.nfine, p.nb, p.W, ws.base1, ws.wbase, ws.sorted, ws.goff);
+  k_sort2<<<g2, 256, sh2, st>>>(ws.l1, Ms, p.cbits, p.ncoarse, p.nfine, p.nb, p.W, ws.base1, ws.wbase, ws.sorted, ws.goff);
   g_kernel_launches += 7;
 }
 

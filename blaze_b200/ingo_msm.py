@@ -156,9 +156,15 @@ class MSMClient(DriverPrimitive):
         check(lib().bz_msm_set_window_bits(self._h, int(c)))
 
     def plan_info(self):
-        out = (ctypes.c_uint32 * 4)()
-        check(lib().bz_msm_plan_info(self._h, out))
-        return {"c": out[0], "windows": out[1], "buckets_per_window": out[2], "segment": out[3]}
+        out = (ctypes.c_uint32 * 8)()
+        check(lib().bz_msm_plan_info_ex(self._h, out))
+        return {"c": out[0], "windows": out[1], "buckets_per_window": out[2], "segment": out[3],
+                "bucket_sets": out[4], "merged_table": bool(out[5]), "merged_table_mib": out[6]}
+
+    def set_precompute(self, mode):
+        """Window-merged table for HBM-resident points: 0 never, 1 from the second MSM on the same points
+        (default), 2 immediately.  Same results in every mode."""
+        check(lib().bz_msm_set_precompute(self._h, int(mode)))
 
     def set_scalars_device(self, dev_ptr, params: MSMParams):
         has, a, o = _hbm(params)

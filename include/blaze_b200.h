@@ -120,6 +120,15 @@ int32_t bz_msm_phase_times(bz_msm* m, float ms[4]);
 int32_t bz_msm_set_window_bits(bz_msm* m, int32_t c);
 /* plan of the last launched task: c, W, buckets/window, segment length */
 int32_t bz_msm_plan_info(bz_msm* m, uint32_t out[4]);
+/* extended plan: c, digit windows (mixed adds per scalar), buckets/set, segment length, bucket sets,
+ * merged flag, MiB held by the window-merged table, level-2 sort bits */
+int32_t bz_msm_plan_info_ex(bz_msm* m, uint32_t out[8]);
+/* Window-merged table for HBM-resident point sets ("precomputed points resident in HBM"): the client
+ * derives 2^(c w) * P_i for every digit window w from the points written with load_data_to_hbm
+ * (msm_api.rs:299-313) so that all windows share one bucket set.  mode 0: never; 1 (default): from the second
+ * MSM over an unchanged point set; 2: immediately.  Results are identical in every mode.  Env BZ_MSM_PRECOMP
+ * sets the default. */
+int32_t bz_msm_set_precompute(bz_msm* m, int32_t mode);
 /* like set_data(points=None) but the scalars already live in device memory (device pointer) */
 int32_t bz_msm_set_scalars_device(bz_msm* m, uint64_t scalars_dev_ptr, uint32_t nof_elements, int32_t has_hbm_addr,
                                   uint64_t hbm_addr, uint64_t hbm_offset);

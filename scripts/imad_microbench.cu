@@ -40,6 +40,17 @@ __global__ void __launch_bounds__(1024) k(uint64_t* out, uint32_t seed, int iter
         uint32_t* w = reinterpret_cast<uint32_t*>(acc);
 #pragma unroll
         for (int i = 0; i < 8; i++) asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(w[i]) : "r"(w[(i + 3) & 7] | 0x80000000u), "r"(b | 0xf0000000u));
+      } else if (MODE == 5) {   // DFMA, 8 independent chains
+        double* w = reinterpret_cast<double*>(acc);
+#pragma unroll
+        for (int i = 0; i < 8; i++) asm volatile("fma.rz.f64 %0, %1, %2, %0;" : "+d"(w[i]) : "d"(w[(i + 3) & 7]), "d"(1.0000001));
+      } else if (MODE == 6) {   // 4 mad.wide + 4 DFMA interleaved (do the two pipes overlap?)  counts all 8
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+          asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"((uint32_t)acc[(i + 1) & 3]), "r"(b));
+        double* w = reinterpret_cast<double*>(acc + 4);
+#pragma unroll
+        for (int i = 0; i < 4; i++) asm volatile("fma.rz.f64 %0, %1, %2, %0;" : "+d"(w[i]) : "d"(w[(i + 1) & 3]), "d"(1.0000001));
       } else if (MODE == 4) {   // 4 mad.wide + 4 independent IADD3-class adds (mix like the field code)
 #pragma unroll
         for (int i = 0; i < 4; i++)
@@ -89,6 +100,8 @@ int main() {
     run<2>("IMAD (mad.lo) independent", w);
     run<3>("IMAD.HI independent", w);
     run<4>("4 IMAD.WIDE + 4 IADD (counts all 8)", w);
+    run<5>("DFMA independent", w);
+    run<6>("4 IMAD.WIDE + 4 DFMA (counts all 8)", w);
   }
   return 0;
 }

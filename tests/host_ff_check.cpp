@@ -33,6 +33,8 @@ static int field_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, in
     case 4: r = ff<F>::inv(x); break;
     case 5: r = ff<F>::neg(x); break;
     case 6: r = ff<F>::dbl(x); break;
+    case 7: r = ff<F>::mul_sub2(x, y, ff<F>::add(x, y), ff<F>::sub(x, y)); break;   // xy - (x+y)(x-y)
+    case 8: r = ff<F>::mul2(x, y, ff<F>::add(x, y), ff<F>::sub(x, y)); break;
     default: return -1;
   }
   store<F>(out, r, nbytes);

@@ -41,6 +41,8 @@ def test_field_ops(hc, name):
             assert fop(hc, fid, 3, a, b, nb) == a * a % p
             assert fop(hc, fid, 5, a, b, nb) == (-a) % p
             assert fop(hc, fid, 6, a, b, nb) == 2 * a % p
+            assert fop(hc, fid, 7, a, b, nb) == (a * b - (a + b) * (a - b)) % p      # fused two-product reduction
+            assert fop(hc, fid, 8, a, b, nb) == (a * b + (a + b) * (a - b)) % p
         for a in vals[1:10]:
             assert fop(hc, fid, 4, a, 0, nb) == pow(a, -1, p)
 

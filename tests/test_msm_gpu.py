@@ -356,3 +356,108 @@ def test_msm_task_queue_two_in_flight(dclient, oracle):
         assert labels == [labels[0], labels[0] + 1, labels[0] + 2]
     finally:
         m.close()
+
+
+# ---- window-merged table (HBM-resident precomputed points: entry (w, i) = 2^(c w) P_i, one bucket set)
+def run_hbm(m, params, sc):
+    m.initialize(params)
+    m.start_process()
+    m.set_data(MSMInput(None, sc, params))
+    m.wait_result()
+    return m.result().result
+
+
+@pytest.mark.parametrize("cname,curve", CURVES)
+@pytest.mark.parametrize("c_bits", [0, 6, 11])
+def test_msm_merged_table_vs_oracle(dclient, oracle, cname, curve, c_bits):
+    c = CURVE_BY_NAME[cname]
+    n = 3000
+    pts, _, _ = chain_points(c, n, seed=201)
+    pts = pts.copy()
+    ps = c.point_size
+    pts[5 * ps:6 * ps] = 0                      # an identity padding record (0, 0)
+    pts[7 * ps:8 * ps] = pts[6 * ps:7 * ps]     # a duplicate point
+    m = MSMClient.new(MSMInit(PointMemoryType.HBM, False, curve), dclient)
+    try:
+        m.set_precompute(2)
+        if c_bits:
+            m.set_window_bits(c_bits)
+        params = MSMParams(n, (0x100, 0))
+        m.load_data_to_hbm(pts, 0x100, 0)
+        for it in range(2):
+            sc = random_scalars(c, n, seed=202 + it)
+            if it == 1:
+                sc[7 * 32:8 * 32] = sc[6 * 32:7 * 32]   # same digit for the duplicate point: doubling inside a bucket
+            got = run_hbm(m, params, sc)
+            plan = m.plan_info()
+            assert plan["merged_table"] and plan["bucket_sets"] == 1 and plan["windows"] > 1, plan
+            if c_bits:
+                assert plan["c"] == c_bits
+            assert got == oracle.msm_pippenger(cname, pts, sc, n), (cname, plan)
+    finally:
+        m.close()
+
+
+def test_msm_merged_table_built_on_reuse(dclient, oracle):
+    """Default policy: the first MSM on a freshly loaded point set runs on the plain table, the table of
+    window multiples is derived when the set is used again; new points invalidate it.  Same bytes either way."""
+    c = CURVE_BY_NAME["BLS12_381"]
+    n = 5000
+    m = MSMClient.new(MSMInit(PointMemoryType.HBM, False, Curve.BLS381), dclient)
+    try:
+        params = MSMParams(n, (0, 0))
+        for rnd in range(2):
+            pts, p0, q = chain_points(c, n, seed=210 + rnd)
+            m.load_data_to_hbm(pts, 0, 0)
+            flags = []
+            for it in range(3):
+                sc = random_scalars(c, n, seed=220 + 10 * rnd + it)
+                assert run_hbm(m, params, sc) == oracle.chain_expected("BLS12_381", p0, q, sc, n)
+                flags.append(m.plan_info()["merged_table"])
+            assert flags == [False, True, True], flags
+        m.set_precompute(0)
+        sc = random_scalars(c, n, seed=240)
+        assert run_hbm(m, params, sc) == oracle.chain_expected("BLS12_381", p0, q, sc, n)
+        assert not m.plan_info()["merged_table"]
+    finally:
+        m.close()
+
+
+def test_msm_merged_table_skewed_and_tiled(dclient, oracle):
+    """Tiled inputs (tests/msm/mod.rs:92-109) and a constant scalar through the merged table: one bucket of
+    the single bucket set receives entries from every window."""
+    c = CURVE_BY_NAME["BLS12_381"]
+    n = 256 * 20 + 3
+    pts256, _, _ = chain_points(c, 256, seed=250)
+    sc256 = random_scalars(c, 256, seed=251)
+    pts = tile(pts256, c.point_size, 256, n)
+    m = MSMClient.new(MSMInit(PointMemoryType.HBM, False, Curve.BLS381), dclient)
+    try:
+        m.set_precompute(2)
+        params = MSMParams(n, (0, 0))
+        m.load_data_to_hbm(pts, 0, 0)
+        sc = tile(sc256, 32, 256, n)
+        assert run_hbm(m, params, sc) == oracle.msm_pippenger("BLS12_381", pts, sc, n)
+        const = np.frombuffer(b"".join([int(0x0123456789abcdef0123456789abcdef0123456789abcdef).to_bytes(32, "little")] * n),
+                              dtype=np.uint8).copy()
+        assert run_hbm(m, params, const) == oracle.msm_pippenger("BLS12_381", pts, const, n)
+    finally:
+        m.close()
+
+
+def test_msm_merged_table_2p20_closed_form(dclient, oracle):
+    c = CURVE_BY_NAME["BLS12_381"]
+    n = 1 << 20
+    from util import seed_points
+    p0, q = seed_points(c, 260)
+    m = MSMClient.new(MSMInit(PointMemoryType.HBM, False, Curve.BLS381), dclient)
+    try:
+        m.set_precompute(2)
+        m.generate_chain_points(p0 + q, 0, n, 0, 0)
+        params = MSMParams(n, (0, 0))
+        for it in range(2):
+            sc = random_scalars(c, n, seed=261 + it)
+            assert run_hbm(m, params, sc) == oracle.chain_expected("BLS12_381", p0, q, sc, n)
+        assert m.plan_info()["merged_table"]
+    finally:
+        m.close()
