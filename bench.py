@@ -402,15 +402,20 @@ def main():
             except Exception:
                 traffic = None
         line = {
-            "metric": METRIC if args.curve == "BLS381" else METRIC.replace("BLS12-381", cname.replace("_", "-")),
+            "metric": METRIC.replace("BLS12-381", cname.replace("_", "-")).replace("2^26", "2^%d" % args.log_n),
             "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "u32 limbs (381-bit Fq Montgomery, 255-bit Fr)",
+            "scaling": "strong", "vs_baseline": None,
+            "dtype": "u32 limbs (%d-bit Fq Montgomery, %d-bit Fr)" % (c.q.bit_length(), c.r.bit_length()),
             "data": "synthetic",
             "config": {
                 "workload": "%s MSM 2^%d, HBM-resident points (configs[1]); points P0+iQ generated on device, "
                             "uniform random canonical scalars" % (cname.replace("_", "-"), args.log_n),
                 "precompute_factor": 1, "window_bits": cbits, "windows": W, "segment": plan["segment"],
+                "bucket_sets": plan["bucket_sets"],
+                "resident_table": ("window-merged: 2^(c*w)*P_i for the %d digit windows derived once from the resident "
+                                   "points (%d MiB of HBM, built in warm-up, not timed), all windows share one bucket set"
+                                   % (W, plan["merged_table_mib"])) if plan["merged_table"] else "points only (Montgomery form)",
                 "parallelism": "point-sharded x%d" % world,
                 "l2": "inputs (2 GiB scalars + 6 GiB points per 2^26) exceed the 126 MB L2; no flush needed",
                 "verified_bit_exact_vs_oracle_closed_form": verified,
@@ -430,8 +435,8 @@ def main():
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "note": "the sweep is integer-multiplier bound, not HBM bound: ncu shows the fmaheavy pipe "
-                                 "(IMAD.WIDE.U32, 4 issue cycles each) ~74% busy and DRAM ~5% "
-                                 "(profiles/r1_ncu_k_accumulate_*.txt)"},
+                                 "(IMAD.WIDE.U32, 4 issue cycles each) ~82% busy and DRAM ~5% "
+                                 "(profiles/r1_ncu_k_accumulate_merged_2p22.txt)"},
         }
         if ntt is not None:
             line["ntt"] = ntt

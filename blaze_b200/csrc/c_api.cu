@@ -343,7 +343,7 @@ static int ilog2_floor(uint64_t v) { int l = 0; while (v >>= 1) l++; return l; }
 static size_t ws_bytes_estimate(const bz_msm* m, uint64_t total, int c, int W) {
   const size_t xb = m->ops->xyzz_bytes;
   const uint64_t nseg = total / 256 + 1;
-  return (size_t)(total * 16 + (uint64_t)W * ((1ull << (c - 1)) + (1ull << 13)) * xb * 9 / 8 + nseg * 2 * (xb + 4) * 33 / 32 + (64ull << 20));
+  return (size_t)(total * 24 + (uint64_t)W * ((1ull << (c - 1)) + (1ull << 13)) * xb * 9 / 8 + nseg * 2 * (xb + 4) * 33 / 32 + (64ull << 20));
 }
 
 static int32_t make_plan(bz_msm* m, uint64_t M, int words_per_scalar, bool merged) {
@@ -393,14 +393,13 @@ static int32_t make_plan(bz_msm* m, uint64_t M, int words_per_scalar, bool merge
       // one bucket set: the reduction is paid once, the table costs W * M entries of HBM
       if ((uint64_t)W * M >= (1ull << 31)) continue;   // entry index = w*M + i must leave bit 31 for the sign
       if ((size_t)W * M * m->ops->affine_bytes + ws_bytes_estimate(m, (uint64_t)W * M, c, 1) > mem_free) continue;
-      double cost = (double)W * (double)M * 1.14 + 6.0 * (double)(1ull << (c - 1));
+      double cost = (double)W * (double)M * 1.06 + 6.0 * (double)(1ull << (c - 1));
       if (cost < best) { best = cost; best_c = c; }
       continue;
     }
-    // measured on B200 (perf_probe, 2^24..2^26): per (scalar, window) the sort costs 0.14 of a mixed add
-    // up to c = 20 and about doubles per two extra bits (more coarse bins -> more scattered writes);
+    // measured on B200 (perf_probe, 2^24..2^26): per (scalar, window) the sort costs about 0.06 of a mixed add;
     // the running-sum reduction costs about 6 mixed-add equivalents per bucket
-    double sort_w = c <= 20 ? 0.14 : 0.14 * (1.0 + 0.5 * (c - 20));
+    double sort_w = 0.06;
     double cost = (double)W * ((double)M * (1.0 + sort_w) + 6.0 * (double)(1ull << (c - 1)));
     // a top window with only a few bits funnels all M entries into a handful of buckets of one
     // coarse bin (one CTA sorts them, long merge chains): avoid such c unless the problem is tiny
@@ -422,23 +421,25 @@ static int32_t make_plan(bz_msm* m, uint64_t M, int words_per_scalar, bool merge
   p.W = merged ? 1 : p.Wd;
   p.Ms = merged ? (uint64_t)p.Wd * M : M;
   const uint64_t Ms = p.Ms;
-  p.nvalues = (1u << (p.c - 1)) + 1;
-  // level-2 (fine) bits: a coarse bin should hold ~32K entries so that the CTA that sorts it owns a
-  // small, quickly-filled output window (L2 merges its 4-byte scatter writes into full sectors)
+  // sort levels (msm_sort.cu): final in-CTA level of fb <= 8 bits over parents of ~8K entries; the other
+  // `rest` key bits go to partition levels of <= 8 bits each
   {
-    int f = 1;
-    while (f < 10 && f < p.c - 1 && ((double)Ms / (double)(1ull << (p.c - 1 - (f + 1)))) <= 32768.0) f++;
-    p.fbits = std::max(1, std::min(f, p.c - 1));
-    while (p.c - 1 - p.fbits > 13) p.fbits++;   // level-1 histogram (2^cbits counters) must fit shared memory
-    if (const char* e = getenv("BZ_MSM_FBITS")) { int v = atoi(e); if (v >= 1 && v <= 12 && v < p.c && p.c - 1 - v <= 13) p.fbits = v; }
+    p.kb = p.c - 1;
+    int rest_t = 0;
+    while (rest_t < 30 && ((double)Ms / (double)(1ull << rest_t)) > 8192.0) rest_t++;
+    int lo = std::max(p.kb - 8, 0), hi = p.kb;
+    if (lo <= 16) hi = std::min(hi, 16);   // two partition levels whenever they suffice
+    p.rest = std::max(lo, std::min(rest_t, hi));
+    p.fb = p.kb - p.rest;
+    p.nlev = std::max(1, (p.rest + 7) / 8);
+    int left = p.rest;
+    for (int l = 0; l < p.nlev; l++) {
+      p.lbits[l] = (left + (p.nlev - l) - 1) / (p.nlev - l);
+      left -= p.lbits[l];
+    }
+    p.nb = 1u << p.kb;
+    p.nvalues = p.nb;
   }
-  p.cbits = p.c - 1 - p.fbits;
-  p.ncoarse = 1 << p.cbits;
-  p.nfine = (1u << p.fbits) + 1;
-  p.nb = (uint32_t)p.ncoarse * p.nfine;
-  p.tile = 65536;
-  while ((Ms + p.tile - 1) / p.tile > 4096) p.tile <<= 1;   // k_colscan1 walks the tiles serially
-  p.ntiles = (uint32_t)((Ms + p.tile - 1) / p.tile);
   uint64_t total = (uint64_t)p.W * Ms;
   // segment length: enough threads to fill the machine several times over, at most 256 entries each
   uint32_t L = 256;
@@ -459,10 +460,33 @@ static int32_t make_plan(bz_msm* m, uint64_t M, int words_per_scalar, bool merge
   cudaError_t e = cudaSuccess;
   auto A = [&](auto** ptr, size_t bytes) { if (e == cudaSuccess) e = ws_alloc(m, ptr, bytes); };
   A(&m->ws.dig, total * 4);
-  A(&m->ws.hmat, (size_t)p.W * p.ntiles * p.ncoarse * 4);
-  A(&m->ws.tot, (size_t)p.W * p.ncoarse * 4);
-  A(&m->ws.base1, (size_t)p.W * (p.ncoarse + 1) * 4);
-  A(&m->ws.l1, total * 8);
+  {
+    size_t words = 0;
+    int consumed = 0;
+    for (int l = 0; l < p.nlev; l++) {
+      consumed += p.lbits[l];
+      // cursor groups: aim at >= 2^16 counters per level so that ~10^5 tiles do not serialise on a few addresses
+      int lg = 0;
+      while (lg < 8 && (((uint64_t)p.W << consumed) << lg) < 65536 && (total >> 13) > (((uint64_t)p.W << consumed) << lg)) lg++;
+      p.lgs[l] = lg;
+      words += (((size_t)p.W << consumed) << lg) + 64;
+    }
+    p.lvl_hist_words = words;
+    uint32_t *h = nullptr, *o = nullptr, *cu = nullptr, *tp = nullptr;
+    A(&h, words * 4);
+    A(&o, words * 4);
+    A(&cu, words * 4);
+    A(&tp, words * 4);
+    size_t at = 0;
+    consumed = 0;
+    for (int l = 0; l < p.nlev && e == cudaSuccess; l++) {
+      consumed += p.lbits[l];
+      m->ws.lvl_hist[l] = h + at; m->ws.lvl_off[l] = o + at; m->ws.lvl_cursor[l] = cu + at; m->ws.lvl_tpref[l] = tp + at;
+      at += (((size_t)p.W << consumed) << p.lgs[l]) + 64;
+    }
+  }
+  A(&m->ws.pairA, total * 8);
+  if (p.nlev > 1) A(&m->ws.pairB, total * 8);
   A(&m->ws.sorted, total * 4);
   A(&m->ws.goff, ((size_t)p.W * p.nb + 1) * 4);
   A((uint8_t**)&m->ws.buckets, (size_t)p.W * p.nb * xb);
@@ -474,7 +498,6 @@ static int32_t make_plan(bz_msm* m, uint64_t M, int words_per_scalar, bool merge
     A(&m->ws.part2_id, (size_t)tot * 2 * 4);
     A((uint8_t**)&m->ws.part2_pt, (size_t)tot * 2 * xb);
   }
-  A(&m->ws.wbase, (size_t)(p.W + 1) * 4);
   if (p.batch_affine) {
     const size_t fb = (size_t)m->ops->fq_bytes, ab = m->ops->affine_list_bytes;
     const uint64_t ng = (uint64_t)p.W * p.nb;
@@ -933,7 +956,7 @@ extern "C" int32_t bz_msm_plan_info_ex(bz_msm* m, uint32_t out[8]) {
   out[4] = m->plan.W;         // bucket sets (1 when the windows are merged)
   out[5] = m->plan.merged;
   out[6] = (uint32_t)(m->wtable_bytes >> 20);   // MiB held by the window-merged table
-  out[7] = m->plan.fbits;
+  out[7] = m->plan.fb | (m->plan.rest << 8) | (m->plan.nlev << 16);
   return BZ_OK;
 }
 extern "C" int32_t bz_msm_plan_info(bz_msm* m, uint32_t out[4]) {

@@ -191,8 +191,11 @@ __global__ void __launch_bounds__(128) k_wtable_level(const AffineT<C>* __restri
 
 // ---------------------------------------------------------------------------------------------
 // bucket accumulation (the dominant kernel)
+// CTAs of 128 threads per SM.  3 (168 registers: the 12-limb curves spill ~170 B/thread around the field calls)
+// beats 2 (228 registers, no spills) by 5% since the field products became calls: the third warp per scheduler
+// covers the fixed-latency waits of the carry chains (measured at 2^24: 68.6 vs 72.2 ms).
 #ifndef BZ_ACC_MINBLOCKS
-#define BZ_ACC_MINBLOCKS 2
+#define BZ_ACC_MINBLOCKS 3
 #endif
 template <class C>
 __global__ void __launch_bounds__(128, BZ_ACC_MINBLOCKS)
@@ -220,7 +223,7 @@ k_accumulate(const AffineT<C>* __restrict__ table, const uint32_t* __restrict__ 
   }
   uint32_t g = lo;
   uint32_t bstart = __ldg(goff + g), bend = __ldg(goff + g + 1);
-  bool skip = (g % nb) == 0;
+  const bool skip = false;   // every bucket slot is a real bucket (zero digits never reach the sort)
   uint32_t id0 = 0xffffffffu, id1 = 0xffffffffu;
   XYZZ<C> acc = G::infinity();
   // software pipeline: the point of entry pos+1 and the index of entry pos+2 are in flight while the
@@ -246,7 +249,6 @@ k_accumulate(const AffineT<C>* __restrict__ table, const uint32_t* __restrict__ 
         bstart = bend;
         bend = __ldg(goff + g + 1);
       } while (bend == pos);
-      skip = (g % nb) == 0;
       acc = G::infinity();
     }
     if (!skip) {
@@ -329,7 +331,7 @@ k_accumulate_tma(const AffineT<C>* __restrict__ table, const uint32_t* __restric
     g = lo;
     bstart = __ldg(goff + g);
     bend = __ldg(goff + g + 1);
-    skip = (g % nb) == 0;
+    skip = false;
   }
   uint32_t id0 = 0xffffffffu, id1 = 0xffffffffu;
   XYZZ<C> acc = G::infinity();
@@ -386,7 +388,6 @@ k_accumulate_tma(const AffineT<C>* __restrict__ table, const uint32_t* __restric
         bstart = bend;
         bend = __ldg(goff + g + 1);
       } while (bend == pos);
-      skip = (g % nb) == 0;
       acc = G::infinity();
     }
     if (!skip) {
@@ -513,15 +514,20 @@ k_reduce_level(const XyzzM<C>* __restrict__ A, const XyzzM<C>* __restrict__ Vin,
 }
 
 // Horner over the window sums, normalise, serialise
+// Slot i of the bucket array holds the bucket of VALUE i + 1 (zero digits never reach the sort), so the window
+// sum is  sum_i (i+1) A[i] = V + S  with V = sum_i i A[i] and S = sum_i A[i], the two top-level outputs.
 template <class C>
-__global__ void k_finish(const XyzzM<C>* __restrict__ win, int W, int c, uint8_t* __restrict__ result) {
+__global__ void k_finish(const XyzzM<C>* __restrict__ winV, const XyzzM<C>* __restrict__ winS, int W, int c,
+                         uint8_t* __restrict__ result) {
   typedef dev<C> D;
   typedef ec<C> G;
   if (blockIdx.x || threadIdx.x) return;
-  XYZZ<C> acc = D::load_xyzz(win + (W - 1));
-  for (int w = W - 2; w >= 0; w--) {
-    for (int d = 0; d < c; d++) acc = G::dbl(acc);
-    XYZZ<C> v = D::load_xyzz(win + w);
+  XYZZ<C> acc = G::infinity();
+  for (int w = W - 1; w >= 0; w--) {
+    if (w != W - 1) for (int d = 0; d < c; d++) acc = G::dbl(acc);
+    XYZZ<C> v = D::load_xyzz(winV + w);
+    G::add(acc, v);
+    v = D::load_xyzz(winS + w);
     G::add(acc, v);
   }
   D::store_result(result, acc);
@@ -667,10 +673,11 @@ struct CurveLaunch {
     const XyzzM<C>* A = buckets;
     const XyzzM<C>* Vin = nullptr;
     uint32_t n = p.nvalues, a_stride = p.nb;
-    int perm_bits = p.cbits;
+    int perm_bits = p.rest;   // level 0 reads value i at its sort slot (i mod 2^rest) * 2^fb + (i >> rest)
     XyzzM<C>* scratch[2] = {(XyzzM<C>*)ws.red_a, (XyzzM<C>*)ws.red_b};
     int level = 0, shift = 0;
     const XyzzM<C>* top = nullptr;
+    const XyzzM<C>* topS = nullptr;
     while (true) {
       const uint32_t s = level == 0 ? p.chunk : 4;
       int log_s = 0;
@@ -679,10 +686,11 @@ struct CurveLaunch {
       XyzzM<C>* Sout = scratch[level & 1];
       XyzzM<C>* Vout = Sout + (size_t)p.W * nch;
       uint32_t nt = (uint32_t)p.W * nch;
-      k_reduce_level<C><<<(nt + 127) / 128, 128, 0, st>>>(A, Vin, n, a_stride, perm_bits, p.nfine, s, nch, p.W, shift, Sout,
+      k_reduce_level<C><<<(nt + 127) / 128, 128, 0, st>>>(A, Vin, n, a_stride, perm_bits, 1u << p.fb, s, nch, p.W, shift, Sout,
                                                         Vout);
       g_kernel_launches += 1;
       top = Vout;
+      topS = Sout;
       if (nch == 1) break;
       A = Sout;
       Vin = Vout;
@@ -692,7 +700,7 @@ struct CurveLaunch {
       shift += log_s;
       level++;
     }
-    k_finish<C><<<1, 32, 0, st>>>(top, p.W, p.c, ws.result);
+    k_finish<C><<<1, 32, 0, st>>>(top, topS, p.W, p.c, ws.result);
   }
   static void build_wtable(void* wtable, uint64_t n, int levels, int c, cudaStream_t st) {
     constexpr int K = 16;

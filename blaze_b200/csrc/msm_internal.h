@@ -36,17 +36,19 @@ struct MsmPlan {
   int merged;              // 1: window-merged table -- digit window w of scalar i uses table entry w*M + i
                            //    (= 2^(c w) P_i, precomputed and resident in HBM) and all windows share one bucket set
   uint64_t Ms;             // sort entries per bucket window: M, or Wd*M when merged (dig[][] read as one flat list)
-  // Bucket VALUES per window are 0 .. 2^(c-1) (nvalues of them; value 0 is never accumulated).  The
-  // sort splits a value b into coarse = b & (ncoarse-1) (LOW bits: level 1) and fine = b >> cbits (level
-  // 2), so skewed digit ranges -- small scalars, a short top window -- still spread over all coarse
-  // bins.  Bucket SLOT of value b is coarse * nfine + fine; nb = ncoarse * nfine slots per window.
-  uint32_t nvalues;        // 2^(c-1) + 1
-  uint32_t nb;             // bucket slots per window = ncoarse * nfine (>= nvalues, the extra ones stay empty)
-  int fbits;               // level-2 (fine) sort bits
-  int cbits;               // level-1 (coarse) bits = c - 1 - fbits
-  int ncoarse;             // level-1 bins = 2^cbits
-  uint32_t nfine;          // level-2 bins = 2^fbits + 1 (the +1 holds the single value 2^(c-1))
-  uint32_t tile, ntiles;   // level-1 tile size / count
+  // Bucket VALUES b per window are 1 .. 2^kb (zero digits are dropped by the sort), kb = c - 1.  The sort key of
+  // b is K = ((b-1) mod 2^rest) << fb | (b-1) >> rest: `rest` bits are consumed by the partition levels (LOW
+  // bits of b-1 first, so skewed digit ranges still spread over all parents), the last fb bits by the final
+  // in-CTA counting sort (msm_sort.cu).  Bucket SLOT of b is K; nb = 2^kb slots per window.
+  int kb;                  // key bits = c - 1
+  int fb;                  // bits of the final level (<= 8)
+  int rest;                // bits of the partition levels = kb - fb
+  int nlev;                // partition levels (>= 1; the first one converts digits to {K, ref} pairs)
+  int lbits[4];            // bits per partition level (sum = rest)
+  int lgs[4];              // log2 of the cursor groups per child at each level (spreads the scatter atomics)
+  size_t lvl_hist_words;   // total words of the per-level child histograms (one allocation, zeroed per task)
+  uint32_t nvalues;        // 2^kb bucket values per window
+  uint32_t nb;             // bucket slots per window = 2^kb
   uint32_t seg_len;        // sorted entries per accumulate thread
   uint64_t nseg;           // number of accumulate segments = ceil(W*M / seg_len)
   int tma_stage;           // 1: k_accumulate_tma (points staged through shared memory by cp.async.bulk), 0: register prefetch
@@ -58,11 +60,12 @@ struct MsmPlan {
 
 struct MsmWorkspace {
   uint32_t* dig;       // [Wd][M]  (merged: one window of Wd*M entries)
-  uint32_t* hmat;      // [W][ntiles][ncoarse]
-  uint32_t* tot;       // [W][ncoarse]
-  uint32_t* base1;     // [W][ncoarse+1]
-  uint32_t* wbase;     // [W+1] start of each window in `sorted` (zero digits are dropped)
-  uint2* l1;           // [W][M]
+  uint32_t* lvl_hist[4];    // per partition level: child counts        [W << (bits consumed so far)]
+  uint32_t* lvl_off[4];     //   exclusive prefix = child offsets (+1 entry: total)
+  uint32_t* lvl_cursor[4];  //   scatter cursors
+  uint32_t* lvl_tpref[4];   //   tile-count prefix of the children (next level's tile map)
+  uint2* pairA;             // [W*Ms] {K, sign|ref} pairs, output of the odd partition levels (1st, 3rd)
+  uint2* pairB;             // [W*Ms] ... of the even ones (null when nlev == 1)
   uint32_t* sorted;    // [W*M]
   uint32_t* goff;      // [W*nb + 1]
   void* buckets;       // [W*nb] XYZZ

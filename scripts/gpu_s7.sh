@@ -1,0 +1,10 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
+O=gpurun_out
+(time timeout 900 python -m pytest tests/test_msm_gpu.py -m gpu -x -q) > $O/s7_tests.log 2>&1; tail -4 $O/s7_tests.log
+export PROBE_CHECK=1 BZ_MSM_PRECOMP=2
+timeout 300 python scripts/perf_probe.py 24 0 > $O/s7_probe_a.log 2>&1; tail -1 $O/s7_probe_a.log
+BLAZE_B200_LIB=$PWD/blaze_b200/libblaze_b200_mb3.so timeout 300 python scripts/perf_probe.py 24 0 > $O/s7_probe_mb3.log 2>&1; tail -1 $O/s7_probe_mb3.log
+export PROBE_CHECK=0
+timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file $O/s7_launches_merged_2p26.csv python scripts/perf_probe.py 26 0 > $O/s7_probe26.log 2>&1
+tail -1 $O/s7_probe26.log
