@@ -494,7 +494,7 @@ static int32_t make_plan(bz_msm* m, uint64_t M, int words_per_scalar, bool merge
   A((uint8_t**)&m->ws.part_pt, (size_t)p.nseg * 2 * xb);
   {
     uint64_t n = p.nseg, tot = 0;
-    while (true) { n = (n + MERGE_GROUP - 1) / MERGE_GROUP; tot += n; if (n == 1) break; }
+    for (int lvl = 0;; lvl++) { const uint64_t g = merge_group(lvl); n = (n + g - 1) / g; tot += n; if (n == 1) break; }
     A(&m->ws.part2_id, (size_t)tot * 2 * 4);
     A((uint8_t**)&m->ws.part2_pt, (size_t)tot * 2 * xb);
   }

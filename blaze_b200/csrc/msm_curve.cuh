@@ -644,13 +644,14 @@ struct CurveLaunch {
     if (ws.ev_acc1) cudaEventRecord(ws.ev_acc1, st);
     {
       // merge tree over the partial list (see k_merge_level)
-      const uint32_t group = MERGE_GROUP;
       const uint32_t* in_id = ws.part_id;
       const XyzzM<C>* in_pt = (const XyzzM<C>*)ws.part_pt;
       uint32_t* out_id = ws.part2_id;
       XyzzM<C>* out_pt = (XyzzM<C>*)ws.part2_pt;
-      uint64_t n_children = p.nseg, span = (uint64_t)p.seg_len * group;
-      while (true) {
+      uint64_t n_children = p.nseg, child_span = p.seg_len;
+      for (int level = 0;; level++) {
+        const uint32_t group = merge_group(level);
+        const uint64_t span = child_span * group;   // sorted positions covered by one group
         uint64_t n_groups = (n_children + group - 1) / group;
         k_merge_level<C><<<(unsigned)((n_groups + 127) / 128), 128, 0, st>>>(ws.goff, ngoff, buckets, in_id, in_pt,
                                                                              n_children, group, span, out_id, out_pt,
@@ -662,7 +663,7 @@ struct CurveLaunch {
         out_id += 2 * n_groups;
         out_pt += 2 * n_groups;
         n_children = n_groups;
-        span *= group;
+        child_span = span;
       }
     }
     }   // !batch_affine

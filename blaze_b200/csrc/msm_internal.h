@@ -18,7 +18,11 @@ enum : int {
   BZ_ERR_SCALAR_RANGE = 1,   // a scalar was not canonical (>= r) / top digit overflow
 };
 
-#define MERGE_GROUP 64   // children per thread in the partial-merge tree
+// children per thread in the partial-merge tree: 64 at the first level (millions of segments: throughput), 8 above
+// (a level costs about `group` sequential additions of latency whatever its size, and the upper levels are tiny)
+#define MERGE_GROUP 64
+#define MERGE_GROUP_UPPER 8
+static inline unsigned merge_group(int level) { return level == 0 ? MERGE_GROUP : MERGE_GROUP_UPPER; }
 
 struct DigitConst {
   uint32_t K[9];      // sum of the half-window offsets (see k_digits)
@@ -71,7 +75,7 @@ struct MsmWorkspace {
   void* buckets;       // [W*nb] XYZZ
   uint32_t* part_id;   // [nseg][2]
   void* part_pt;       // [nseg][2] XYZZ
-  uint32_t* part2_id;  // merge-tree levels above the segments: [sum_k ceil(nseg / MERGE_GROUP^k)][2]
+  uint32_t* part2_id;  // merge-tree levels above the segments: [sum over levels of the group counts][2]
   void* part2_pt;
   void* red_a;         // [2][W*nchunks] XYZZ: S and V outputs of the even reduction levels
   void* red_b;         // ... of the odd levels
