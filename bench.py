@@ -50,6 +50,7 @@ def parse():
                     help="headline metric is BLS381; the other curves run the same workload (e.g. configs[4])")
     ap.add_argument("--no-ntt", action="store_true", help="skip the secondary metric (2^27 NTT ms)")
     ap.add_argument("--ntt-log-n", type=int, default=27)
+    ap.add_argument("--no-dma", action="store_true", help="skip the DMA-mode measurement (BN254 2^24, configs[2])")
     return ap.parse_args()
 
 
@@ -192,6 +193,54 @@ def ntt_section(args, bz, torch, dist, dc, rank, world, local):
             "layout": layout, "semantics": "arkworks Radix2EvaluationDomain::fft (natural in/out), forward",
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s per GPU", "frac": gbs / hbm_peak,
                          "algorithmic_bytes": npass * 2 * n * 32}}
+
+
+def dma_section(args, bz, torch, dc):
+    """BASELINE.json configs[2]: BN254 MSM 2^24 in DMA mode -- points AND scalars come from (pinned) host memory
+    with every call (msm_api.rs:175-202), so the H2D copies and the canonical->Montgomery table build are
+    inside every timed step.  Checked against the oracle's closed form."""
+    import numpy as np
+    from oracle import capi
+    from oracle.py import curves
+    from util import random_scalars, seed_points
+    c = curves.BN254
+    log_n = 24
+    n = 1 << log_n
+    p0, q = seed_points(c, 91)
+    gen = bz.MSMClient.new(bz.MSMInit(bz.PointMemoryType.HBM, False, bz.Curve.BN254), dc)
+    try:
+        gen.generate_chain_points(p0 + q, 0, n, 0x100000000, 0)
+        pts_pinned = torch.empty(n * c.point_size, dtype=torch.uint8).pin_memory()
+        pts_pinned.numpy()[:] = np.frombuffer(gen.get_data_from_hbm(n * c.point_size, 0x100000000, 0), dtype=np.uint8)
+    finally:
+        gen.close()
+    sc_np = random_scalars(c, n, seed=92)
+    sc_pinned = torch.empty(n * 32, dtype=torch.uint8).pin_memory()
+    sc_pinned.numpy()[:] = sc_np
+    m = bz.MSMClient.new(bz.MSMInit(bz.PointMemoryType.DMA, False, bz.Curve.BN254), dc)
+    try:
+        params = bz.MSMParams(n, None)
+        walls, dev = [], []
+        res = None
+        for i in range(2 + max(3, args.steps)):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            m.initialize(params)
+            m.start_process()
+            m.set_data(bz.MSMInput((pts_pinned.data_ptr(), n * c.point_size), (sc_pinned.data_ptr(), n * 32), params))
+            m.wait_result()
+            res = m.result().result
+            if i >= 2:
+                walls.append(time.perf_counter() - t0)
+                dev.append(m.phase_times()["total"])
+        ok = bool(res == capi.chain_expected("BN254", p0, q, sc_np, n))
+        ms = 1e3 * sum(walls) / len(walls)
+        return {"workload": "BN254 MSM 2^24, DMA mode (configs[2]): points + scalars streamed from pinned host memory every call",
+                "ms_per_call": ms, "scalar_mults_per_s": n / (ms / 1e3), "device_pipeline_ms": sum(dev) / len(dev),
+                "h2d_bytes_per_call": n * (c.point_size + 32), "verified_bit_exact_vs_oracle_closed_form": ok,
+                "plan": m.plan_info()}
+    finally:
+        m.close()
 
 
 def run_reference(args, rank, world):
@@ -385,6 +434,13 @@ def main():
         except Exception as e:     # the headline line must still be printed
             ntt = {"error": repr(e)}
 
+    dma = None
+    if world == 1 and not args.no_dma:
+        try:
+            dma = dma_section(args, bz, torch, dc)
+        except Exception as e:
+            dma = {"error": repr(e)}
+
     if rank == 0:
         plan = m.plan_info()
         W, cbits = plan["windows"], plan["c"]
@@ -440,6 +496,8 @@ def main():
         }
         if ntt is not None:
             line["ntt"] = ntt
+        if dma is not None:
+            line["dma_mode"] = dma
         if world == 1 and not args.no_cpu_baseline:
             from oracle import capi
             capi.build()

@@ -77,6 +77,12 @@ BZ_DI uint64_t addc_cc64(uint64_t a, uint64_t b) {
 BZ_DI uint64_t addc64(uint64_t a, uint64_t b) {
   uint64_t r; asm volatile("addc.u64 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
 }
+// m * (2^32 - 1) = (m << 32) - m without the multiplier (asm: the compiler would turn the C form back into a product)
+BZ_DI uint64_t mul_2p32m1(uint32_t m) {
+  uint64_t r;
+  asm("{\n\t.reg .u32 lo, hi;\n\tsub.cc.u32 lo, 0, %1;\n\tsubc.u32 hi, %1, 0;\n\tmov.b64 %0, {lo, hi};\n\t}" : "=l"(r) : "r"(m));
+  return r;
+}
 // a + (CC << 32): consume the carry flag into the HIGH 32-bit half of a 64-bit word (one IADD3.X)
 BZ_DI uint64_t addc_hi32(uint64_t a) {
   uint64_t r;
@@ -121,6 +127,7 @@ inline uint64_t add_cc64(uint64_t a, uint64_t b) { return add3_64(a, b, 0, true)
 inline uint64_t addc_cc64(uint64_t a, uint64_t b) { return add3_64(a, b, flag(), true); }
 inline uint64_t addc64(uint64_t a, uint64_t b) { return add3_64(a, b, flag(), false); }
 inline uint64_t addc_hi32(uint64_t a) { return a + ((uint64_t)flag() << 32); }
+inline uint64_t mul_2p32m1(uint32_t m) { return ((uint64_t)m << 32) - (uint64_t)m; }
 #endif
 
 }  // namespace cc

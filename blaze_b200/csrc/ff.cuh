@@ -94,6 +94,16 @@ struct ff {
   }
   BZ_HDI static E neg(const E& a) { return sub(zero(), a); }
 
+  // m * p[K] for the two lowest modulus limbs: 1 and 2^32 - 1 (Fr of BLS12-381 has both, several fields the
+  // first) need no multiplier instruction
+  template <int K>
+  BZ_HDI static uint64_t mod_times(uint32_t m) {
+    constexpr uint32_t c = K == 0 ? F::MOD0 : F::MOD1;
+    if constexpr (c == 1u) return (uint64_t)m;
+    else if constexpr (c == 0xffffffffu) return cc::mul_2p32m1(m);
+    else return cc::mul_wide(F::mod()[K], m);
+  }
+
   // ---- Montgomery product (see header) ----
   // One multiplier limb.  E ("even") holds 64-bit columns (2k, 2k+1), O ("odd") columns
   // (2k+1, 2k+2):  T = E + 2^32 * O.  On entry of a non-first step O is the previous step's E,
@@ -121,11 +131,11 @@ struct ff {
       Ov[NW - 1] = cc::addc_hi32(Ov[NW - 1]);   // carry out of the even chain = bit 32 of the top odd word
     }
     uint32_t m = (uint32_t)Ev[0] * F::INV;
-    Ov[0] = cc::add_cc64(Ov[0], cc::mul_wide(F::mod()[1], m));
+    Ov[0] = cc::add_cc64(Ov[0], mod_times<1>(m));
 #pragma unroll
     for (int k = 1; k < NW - 1; k++) Ov[k] = cc::addc_cc64(Ov[k], cc::mul_wide(F::mod()[2 * k + 1], m));
     Ov[NW - 1] = cc::addc64(Ov[NW - 1], cc::mul_wide(F::mod()[N - 1], m));
-    Ev[0] = cc::add_cc64(Ev[0], cc::mul_wide(F::mod()[0], m));
+    Ev[0] = cc::add_cc64(Ev[0], mod_times<0>(m));
 #pragma unroll
     for (int k = 1; k < NW; k++) Ev[k] = cc::addc_cc64(Ev[k], cc::mul_wide(F::mod()[2 * k], m));
     Ov[NW - 1] = cc::addc_hi32(Ov[NW - 1]);
@@ -304,11 +314,11 @@ struct ff {
       Ov[NW - 1] = cc::addc_hi32(Ov[NW - 1]);   // carry out of the even chain = bit 32 of the top odd word
     }
     uint32_t m = (uint32_t)Ev[0] * F::INV;
-    Ov[0] = cc::add_cc64(Ov[0], cc::mul_wide(F::mod()[1], m));
+    Ov[0] = cc::add_cc64(Ov[0], mod_times<1>(m));
 #pragma unroll
     for (int k = 1; k < NW - 1; k++) Ov[k] = cc::addc_cc64(Ov[k], cc::mul_wide(F::mod()[2 * k + 1], m));
     Ov[NW - 1] = cc::addc64(Ov[NW - 1], cc::mul_wide(F::mod()[N - 1], m));
-    Ev[0] = cc::add_cc64(Ev[0], cc::mul_wide(F::mod()[0], m));
+    Ev[0] = cc::add_cc64(Ev[0], mod_times<0>(m));
 #pragma unroll
     for (int k = 1; k < NW; k++) Ev[k] = cc::addc_cc64(Ev[k], cc::mul_wide(F::mod()[2 * k], m));
     Ov[NW - 1] = cc::addc_hi32(Ov[NW - 1]);

@@ -110,8 +110,12 @@ struct PartArgs {
   uint2* out;
 };
 
+#ifndef PART_TILE
 #define PART_TILE 8192
+#endif
+#ifndef PART_THREADS
 #define PART_THREADS 512
+#endif
 #define PART_EPT (PART_TILE / PART_THREADS)
 
 __device__ __forceinline__ uint32_t sort_key(uint32_t b, int rest, int fb) {   // b >= 1

@@ -67,6 +67,8 @@ struct nt {
   __device__ __forceinline__ static E tw(const NttTables& t, uint64_t e) {
     uint32_t lo = (uint32_t)(e & ((1u << t.lo_bits) - 1));
     uint32_t hi = (uint32_t)(e >> t.lo_bits);
+    if (lo == 0) return ld(t.hi + 2 * (size_t)hi);   // hi[0] = 1; exponents that are multiples of 2^lo_bits (the
+                                                      // per-CTA w_R table of a large transform) need no product
     E a = ld(t.lo + 2 * (size_t)lo);
     if (hi == 0) return a;
     E b = ld(t.hi + 2 * (size_t)hi);
