@@ -298,6 +298,12 @@ struct bz_msm {
   uint64_t table_uses = 0;       // MSMs launched on the current arena table
   uint8_t* dma_points = nullptr;
   size_t dma_points_cap = 0;
+  // DMA mode: the points travel on the copy stream BEHIND the scalars, so digits + sort of the task run while
+  // the (larger) point copy is still in flight; the table is built on the work stream once they have landed
+  bool table_pending = false;
+  uint64_t table_pending_n = 0;
+  cudaEvent_t ev_points_copied = nullptr, ev_points_consumed = nullptr;
+  bool points_consumed_valid = false;
   // scalar ingest: two staging buffers filled on a dedicated copy stream, so the H2D of task k+1
   // overlaps the kernels of task k (the reference's task queue allows exactly that pipelining)
   uint32_t* scalars_dev[2] = {nullptr, nullptr};
@@ -551,6 +557,8 @@ extern "C" int32_t bz_msm_new(bz_dclient* dc, int32_t curve, int32_t mem_type, i
     cudaEventCreateWithFlags(&m->ev_copied[b], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&m->ev_consumed[b], cudaEventDisableTiming);
   }
+  cudaEventCreateWithFlags(&m->ev_points_copied, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&m->ev_points_consumed, cudaEventDisableTiming);
   if (cudaHostAlloc((void**)&m->pinned, (size_t)RESULT_SLOTS * RESULT_SLOT_BYTES, cudaHostAllocDefault) != cudaSuccess) {
     delete m;
     return fail(BZ_ERR_NO_DEVICE, "pinned allocation failed");
@@ -578,6 +586,8 @@ extern "C" int32_t bz_msm_free(bz_msm* m) {
     if (m->ev_copied[b]) cudaEventDestroy(m->ev_copied[b]);
     if (m->ev_consumed[b]) cudaEventDestroy(m->ev_consumed[b]);
   }
+  if (m->ev_points_copied) cudaEventDestroy(m->ev_points_copied);
+  if (m->ev_points_consumed) cudaEventDestroy(m->ev_points_consumed);
   if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
   if (m->pinned) cudaFreeHost(m->pinned);
   for (auto& e : m->ev) if (e) cudaEventDestroy(e);
@@ -653,6 +663,8 @@ static int32_t ensure_wtable(bz_msm* m, uint64_t n) {
   return BZ_OK;
 }
 
+static int32_t build_table(bz_msm* m, const uint8_t* raw_dev, uint64_t n_points);
+
 // enqueue the whole pipeline for one task on the client's stream
 static int32_t launch_task(bz_msm* m) {
   bz_dclient* dc = m->dc;
@@ -693,6 +705,14 @@ static int32_t launch_task(bz_msm* m) {
   if (m->stage_cur >= 0) {   // k_digits (the only reader of the staging buffer) is queued: mark it consumed
     cudaEventRecord(m->ev_consumed[m->stage_cur], st);
     m->consumed_valid[m->stage_cur] = true;
+  }
+  if (m->table_pending) {   // DMA mode: the points were copied behind the scalars; convert them now
+    CUDA_TRY(BZ_ERR_UNKNOWN, cudaStreamWaitEvent(st, m->ev_points_copied, 0));
+    rc = build_table(m, m->dma_points, m->table_pending_n);
+    if (rc) return rc;
+    cudaEventRecord(m->ev_points_consumed, st);
+    m->points_consumed_valid = true;
+    m->table_pending = false;
   }
   cudaEventRecord(m->ev[1], st);
   m->ops->bucket_phase(m->plan, m->ws, merged ? m->wtable : m->table, st);
@@ -769,9 +789,7 @@ static int32_t stage_scalars(bz_msm* m, const uint8_t* scalars, size_t len) {
   if (m->consumed_valid[b]) CUDA_TRY(BZ_ERR_WRITE, cudaStreamWaitEvent(m->copy_stream, m->ev_consumed[b], 0));
   CUDA_TRY(BZ_ERR_WRITE, cudaMemcpyAsync(m->scalars_dev[b], scalars, len, cudaMemcpyHostToDevice, m->copy_stream));
   CUDA_TRY(BZ_ERR_WRITE, cudaEventRecord(m->ev_copied[b], m->copy_stream));
-  // the caller may drop its buffer when we return (move-in semantics): block the HOST on the copy
-  // stream only -- the work stream keeps running the previous task meanwhile
-  CUDA_TRY(BZ_ERR_WRITE, cudaStreamSynchronize(m->copy_stream));
+  // (the host blocks on the copy stream at the end of set_data, after the task has been queued)
   m->scalars_src = m->scalars_dev[b];
   m->stage_cur = b;
   return BZ_OK;
@@ -793,6 +811,7 @@ static int32_t set_data_common(bz_msm* m, const uint8_t* points, size_t points_l
   const uint64_t npts = n * m->factor;
   if (npts >= (1ull << 31)) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "too many points");
   // a new input replaces a previous un-consumed one only after the stream has drained it
+  bool dma_points_now = false;
   if (points && !has_hbm_addr) {
     // DMA mode: points streamed with the call (msm_api.rs:175-202)
     if (m->dma_points_cap < points_len) {
@@ -802,11 +821,8 @@ static int32_t set_data_common(bz_msm* m, const uint8_t* points, size_t points_l
       CUDA_TRY(BZ_ERR_WRITE, cudaMalloc((void**)&m->dma_points, points_len));
       m->dma_points_cap = points_len;
     }
-    CUDA_TRY(BZ_ERR_WRITE, cudaMemcpyAsync(m->dma_points, points, points_len, cudaMemcpyHostToDevice, m->dc->stream));
-    CUDA_TRY(BZ_ERR_WRITE, cudaStreamSynchronize(m->dc->stream));   // the caller may drop `points` on return
-    rc = build_table(m, m->dma_points, npts);
-    if (rc) return rc;
     m->table_from_arena = false;
+    dma_points_now = true;   // copied below, behind the scalars
   } else {
     uint64_t a = hbm_addr + hbm_offset;
     if (points) {
@@ -825,10 +841,25 @@ static int32_t set_data_common(bz_msm* m, const uint8_t* points, size_t points_l
     m->stage_cur = -1;
     m->scalars_src = reinterpret_cast<const uint32_t*>(scalars_dev_ptr);
   }
+  if (dma_points_now) {
+    // do not overwrite the point buffer before the table of the previous task has been built from it
+    if (m->points_consumed_valid) CUDA_TRY(BZ_ERR_WRITE, cudaStreamWaitEvent(m->copy_stream, m->ev_points_consumed, 0));
+    CUDA_TRY(BZ_ERR_WRITE, cudaMemcpyAsync(m->dma_points, points, points_len, cudaMemcpyHostToDevice, m->copy_stream));
+    CUDA_TRY(BZ_ERR_WRITE, cudaEventRecord(m->ev_points_copied, m->copy_stream));
+    m->table_pending = true;
+    m->table_pending_n = npts;
+  }
   m->data_M = npts;
   m->data_ready = true;
-  if (m->pending_tasks > 0) return launch_task(m);
-  return BZ_OK;
+  rc = BZ_OK;
+  if (m->pending_tasks > 0) rc = launch_task(m);
+  // the caller may drop its buffers when we return (move-in semantics): block the HOST on the copy stream only --
+  // the work stream keeps running (the previous task, or this task's digits + sort while the points still travel)
+  if (scalars_host || dma_points_now) {
+    cudaError_t ce = cudaStreamSynchronize(m->copy_stream);
+    if (ce != cudaSuccess && rc == BZ_OK) rc = fail(BZ_ERR_WRITE, "host-to-device copy failed: %s", cudaGetErrorString(ce));
+  }
+  return rc;
 }
 
 extern "C" int32_t bz_msm_set_data(bz_msm* m, const uint8_t* points, size_t points_len, const uint8_t* scalars, size_t scalars_len,

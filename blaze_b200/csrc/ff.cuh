@@ -213,7 +213,7 @@ struct ff {
 #if defined(BZ_NOINLINE_MUL) && defined(__CUDACC__)
       return mul2_call(a, b, c, d);
 #else
-      return mul2_inline(a, b, c, d);
+      return mul2_sel(a, b, c, d);
 #endif
     }
   }
@@ -225,6 +225,159 @@ struct ff {
 #endif
   }
 
+  // ---- Karatsuba product + reduction-only Montgomery (BZ_KARATSUBA; fields with N % 4 == 0) -----------------
+  // The interleaved product above spends N^2 multiplier instructions on a*b and N^2 + N on the reduction.
+  // Splitting the two lets the product be one level of Karatsuba -- three H x H products, H = N/2, i.e.
+  // 3/4 N^2 -- at the price of ~10 N plain adds, which go to the otherwise idle ALU pipe; the sum of two
+  // products (mul2) shares one reduction as before.
+  //
+  // z[0..2H) = a[0..H) * b[0..H): schoolbook on the E/O columns, one output limb per row
+  template <int H>
+  BZ_HDI static void prod_half(const uint32_t* a, const uint32_t* b, uint32_t* z) {
+    static_assert(H % 2 == 0, "half width must be even");
+    constexpr int HW = H / 2;
+    uint64_t X[HW], Y[HW];   // X starts in the even role; the roles swap every row (that is the shift by 32 bits)
+#pragma unroll
+    for (int i = 0; i < H; i++) {
+      uint64_t* Ev = (i & 1) ? Y : X;
+      uint64_t* Ov = (i & 1) ? X : Y;
+      const uint32_t bi = b[i];
+      if (i == 0) {
+#pragma unroll
+        for (int k = 0; k < HW; k++) {
+          Ov[k] = cc::mul_wide(a[2 * k + 1], bi);
+          Ev[k] = cc::mul_wide(a[2 * k], bi);
+        }
+      } else {
+        uint64_t h = Ov[0] >> 32;
+        if (HW > 1) {
+          Ov[0] = cc::add_cc64(Ov[1], cc::mul_wide(a[1], bi));
+#pragma unroll
+          for (int k = 1; k < HW - 1; k++) Ov[k] = cc::addc_cc64(Ov[k + 1], cc::mul_wide(a[2 * k + 1], bi));
+          Ov[HW - 1] = cc::addc64(0ull, cc::mul_wide(a[H - 1], bi));
+        } else {
+          Ov[0] = cc::mul_wide(a[1], bi);
+        }
+        Ev[0] = cc::add_cc64(Ev[0], cc::mad_wide(a[0], bi, h));
+#pragma unroll
+        for (int k = 1; k < HW; k++) Ev[k] = cc::addc_cc64(Ev[k], cc::mul_wide(a[2 * k], bi));
+        Ov[HW - 1] = cc::addc_hi32(Ov[HW - 1]);
+      }
+      z[i] = (uint32_t)Ev[0];
+    }
+    // H is even: the last row had Y in the even role; what is left is (Y >> 32) + X  (H limbs, no carry out)
+    z[H] = cc::add_cc((uint32_t)(Y[0] >> 32), (uint32_t)X[0]);
+#pragma unroll
+    for (int j = 1; j < H - 1; j++) {
+      uint32_t y = ((j + 1) & 1) ? (uint32_t)(Y[(j + 1) / 2] >> 32) : (uint32_t)Y[(j + 1) / 2];
+      uint32_t x = (j & 1) ? (uint32_t)(X[j / 2] >> 32) : (uint32_t)X[j / 2];
+      z[H + j] = cc::addc_cc(y, x);
+    }
+    z[2 * H - 1] = cc::addc((uint32_t)(X[HW - 1] >> 32), 0u);
+  }
+  // T[0..2N) = a * b, one level of Karatsuba
+  BZ_HDI static void prod_kara(const uint32_t* a, const uint32_t* b, uint32_t* T) {
+    constexpr int H = N / 2;
+    uint32_t sa[H], sb[H], z1[2 * H + 1];
+    prod_half<H>(a, b, T);                   // z0
+    prod_half<H>(a + H, b + H, T + 2 * H);   // z2
+    sa[0] = cc::add_cc(a[0], a[H]);
+#pragma unroll
+    for (int i = 1; i < H; i++) sa[i] = cc::addc_cc(a[i], a[H + i]);
+    const uint32_t ca = cc::addc(0u, 0u);
+    sb[0] = cc::add_cc(b[0], b[H]);
+#pragma unroll
+    for (int i = 1; i < H; i++) sb[i] = cc::addc_cc(b[i], b[H + i]);
+    const uint32_t cb = cc::addc(0u, 0u);
+    prod_half<H>(sa, sb, z1);
+    // (sa + ca 2^(32H)) (sb + cb 2^(32H)) = sa sb + (ca sb + cb sa) 2^(32H) + ca cb 2^(64H)
+    const uint32_t ma = 0u - ca, mb = 0u - cb;
+    z1[H] = cc::add_cc(z1[H], sb[0] & ma);
+#pragma unroll
+    for (int i = 1; i < H; i++) z1[H + i] = cc::addc_cc(z1[H + i], sb[i] & ma);
+    z1[2 * H] = cc::addc(ca & cb, 0u);
+    z1[H] = cc::add_cc(z1[H], sa[0] & mb);
+#pragma unroll
+    for (int i = 1; i < H; i++) z1[H + i] = cc::addc_cc(z1[H + i], sa[i] & mb);
+    z1[2 * H] = cc::addc(z1[2 * H], 0u);
+    // z1 -= z0 + z2  (the result is the non-negative middle term)
+    z1[0] = cc::sub_cc(z1[0], T[0]);
+#pragma unroll
+    for (int i = 1; i < 2 * H; i++) z1[i] = cc::subc_cc(z1[i], T[i]);
+    z1[2 * H] = cc::subc(z1[2 * H], 0u);
+    z1[0] = cc::sub_cc(z1[0], T[2 * H]);
+#pragma unroll
+    for (int i = 1; i < 2 * H; i++) z1[i] = cc::subc_cc(z1[i], T[2 * H + i]);
+    z1[2 * H] = cc::subc(z1[2 * H], 0u);
+    // T += z1 << (32 H)
+    T[H] = cc::add_cc(T[H], z1[0]);
+#pragma unroll
+    for (int i = 1; i <= 2 * H; i++) T[H + i] = cc::addc_cc(T[H + i], z1[i]);
+#pragma unroll
+    for (int i = 3 * H + 1; i < 4 * H - 1; i++) T[i] = cc::addc_cc(T[i], 0u);
+    T[4 * H - 1] = cc::addc(T[4 * H - 1], 0u);
+  }
+  // r = T / R mod p for T < 2 p^2 (2N limbs): N reduction rows on the low half, then the high half is added
+  BZ_HDI static E redc(const uint32_t* T) {
+    constexpr int NW = N / 2;
+    uint64_t X[NW], Y[NW];
+#pragma unroll
+    for (int k = 0; k < NW; k++) { X[k] = (uint64_t)T[2 * k] | ((uint64_t)T[2 * k + 1] << 32); Y[k] = 0; }
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      uint64_t* Ev = (i & 1) ? Y : X;
+      uint64_t* Ov = (i & 1) ? X : Y;
+      uint64_t h = 0;
+      if (i != 0) {
+        h = Ov[0] >> 32;
+#pragma unroll
+        for (int k = 0; k < NW - 1; k++) Ov[k] = Ov[k + 1];
+        Ov[NW - 1] = 0;
+      }
+      const uint32_t m = ((uint32_t)Ev[0] + (uint32_t)h) * F::INV;
+      Ov[0] = cc::add_cc64(Ov[0], mod_times<1>(m));
+#pragma unroll
+      for (int k = 1; k < NW - 1; k++) Ov[k] = cc::addc_cc64(Ov[k], cc::mul_wide(F::mod()[2 * k + 1], m));
+      Ov[NW - 1] = cc::addc64(Ov[NW - 1], cc::mul_wide(F::mod()[N - 1], m));
+      Ev[0] = cc::add_cc64(Ev[0], mod_times<0>(m) + h);   // m p0 + h < 2^64
+#pragma unroll
+      for (int k = 1; k < NW; k++) Ev[k] = cc::addc_cc64(Ev[k], cc::mul_wide(F::mod()[2 * k], m));
+      Ov[NW - 1] = cc::addc_hi32(Ov[NW - 1]);
+    }
+    // N is even: the last row had Y in the even role: (T_lo + M p) / R = X + (Y >> 32); then + T_hi
+    E r;
+    r.v[0] = cc::add_cc((uint32_t)X[0], (uint32_t)(Y[0] >> 32));
+#pragma unroll
+    for (int j = 1; j < N - 1; j++) {
+      uint32_t e = (j & 1) ? (uint32_t)(X[j / 2] >> 32) : (uint32_t)X[j / 2];
+      uint32_t o = ((j + 1) & 1) ? (uint32_t)(Y[(j + 1) / 2] >> 32) : (uint32_t)Y[(j + 1) / 2];
+      r.v[j] = cc::addc_cc(e, o);
+    }
+    r.v[N - 1] = cc::addc((uint32_t)(X[NW - 1] >> 32), 0u);
+    r.v[0] = cc::add_cc(r.v[0], T[N]);
+#pragma unroll
+    for (int j = 1; j < N - 1; j++) r.v[j] = cc::addc_cc(r.v[j], T[N + j]);
+    r.v[N - 1] = cc::addc(r.v[N - 1], T[2 * N - 1]);
+    final_sub(r.v);
+    return r;
+  }
+  BZ_HDI static E mul_kara(const E& a, const E& b) {
+    uint32_t T[2 * N];
+    prod_kara(a.v, b.v, T);
+    return redc(T);
+  }
+  BZ_HDI static E mul2_kara(const E& a, const E& b, const E& c, const E& d) {
+    static_assert(F::BITS + 2 <= 32 * N, "sum of two products needs two spare bits");
+    uint32_t T[2 * N], U[2 * N];
+    prod_kara(a.v, b.v, T);
+    prod_kara(c.v, d.v, U);
+    T[0] = cc::add_cc(T[0], U[0]);
+#pragma unroll
+    for (int i = 1; i < 2 * N - 1; i++) T[i] = cc::addc_cc(T[i], U[i]);
+    T[2 * N - 1] = cc::addc(T[2 * N - 1], U[2 * N - 1]);
+    return redc(T);
+  }
+
   // r = a*b/R mod p.  With BZ_NOINLINE_MUL the product and the square are real function calls (operands
   // and result travel in registers, ~35 MOVs per call): the unrolled bodies are 400 / 330 instructions, so
   // a mixed add with ten of them inlined is ~62 KB of code per loop iteration -- twice the SM's 32 KB
@@ -233,7 +386,7 @@ struct ff {
 #if defined(BZ_NOINLINE_MUL) && defined(__CUDACC__)
     return mul_call(a, b);
 #else
-    return mul_inline(a, b);
+    return mul_sel(a, b);
 #endif
   }
   BZ_HDI static E sqr(const E& a) {
@@ -244,10 +397,26 @@ struct ff {
 #endif
   }
 #ifdef __CUDACC__
-  static __device__ __noinline__ E mul_call(const E a, const E b) { return mul_inline(a, b); }
+  static __device__ __noinline__ E mul_call(const E a, const E b) { return mul_sel(a, b); }
   static __device__ __noinline__ E sqr_call(const E a) { return sqr_inline(a); }
-  static __device__ __noinline__ E mul2_call(const E a, const E b, const E c, const E d) { return mul2_inline(a, b, c, d); }
+  static __device__ __noinline__ E mul2_call(const E a, const E b, const E c, const E d) { return mul2_sel(a, b, c, d); }
 #endif
+  BZ_HDI static E mul_sel(const E& a, const E& b) {
+#ifdef BZ_KARATSUBA
+    if constexpr (N % 4 == 0 && N >= BZ_KARATSUBA) return mul_kara(a, b);
+    else return mul_inline(a, b);
+#else
+    return mul_inline(a, b);
+#endif
+  }
+  BZ_HDI static E mul2_sel(const E& a, const E& b, const E& c, const E& d) {
+#ifdef BZ_KARATSUBA
+    if constexpr (N % 4 == 0 && N >= BZ_KARATSUBA) return mul2_kara(a, b, c, d);
+    else return mul2_inline(a, b, c, d);
+#else
+    return mul2_inline(a, b, c, d);
+#endif
+  }
   BZ_HDI static E mul_inline(const E& a, const E& b) {
     constexpr int NW = N / 2;
     uint64_t Ev[NW], Ov[NW];

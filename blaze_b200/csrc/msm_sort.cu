@@ -242,31 +242,39 @@ __global__ void __launch_bounds__(PART_THREADS) k_part_scatter(PartArgs a) {
   const uint32_t mask = (uint32_t)nchild - 1;
   uint32_t K[PART_EPT], pay[PART_EPT], rk[PART_EPT];   // rk = child << 16 | rank (rank < 8192), 0xffffffff = no entry
   const uint64_t win_base = FIRST ? (uint64_t)parent * a.Ms : 0;
+  // all loads of the tile first (independent: 16 in flight per thread), then the ranking
 #pragma unroll
   for (int j = 0; j < PART_EPT; j++) {
     const uint64_t i = lo + (uint64_t)j * PART_THREADS + threadIdx.x;
-    rk[j] = 0xffffffffu;
     K[j] = 0;
     pay[j] = 0;
     if (i < hi) {
-      bool have = true;
       if (FIRST) {
-        uint32_t e = __ldg(a.dig + i);
-        uint32_t b = e & 0x7fffffffu;
-        have = b != 0;
-        if (have) {
-          K[j] = sort_key(b, a.rest, a.fb);
-          pay[j] = (e & 0x80000000u) | (uint32_t)(i - win_base);
-        }
+        pay[j] = __ldg(a.dig + i);   // raw digit entry for now
       } else {
         uint2 e = a.in[i];
         K[j] = e.x;
         pay[j] = e.y;
       }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < PART_EPT; j++) {
+    const uint64_t i = lo + (uint64_t)j * PART_THREADS + threadIdx.x;
+    rk[j] = 0xffffffffu;
+    bool have = i < hi;
+    if (FIRST && have) {
+      const uint32_t e = pay[j];
+      const uint32_t b = e & 0x7fffffffu;
+      have = b != 0;   // zero digits are dropped
       if (have) {
-        uint32_t ch = (K[j] >> a.kshift) & mask;
-        rk[j] = (ch << 16) | atomicAdd(&cnt[ch], 1u);
+        K[j] = sort_key(b, a.rest, a.fb);
+        pay[j] = (e & 0x80000000u) | (uint32_t)(i - win_base);
       }
+    }
+    if (have) {
+      uint32_t ch = (K[j] >> a.kshift) & mask;
+      rk[j] = (ch << 16) | atomicAdd(&cnt[ch], 1u);
     }
   }
   __syncthreads();

@@ -43,6 +43,8 @@ def test_field_ops(hc, name):
             assert fop(hc, fid, 6, a, b, nb) == 2 * a % p
             assert fop(hc, fid, 7, a, b, nb) == (a * b - (a + b) * (a - b)) % p      # fused two-product reduction
             assert fop(hc, fid, 8, a, b, nb) == (a * b + (a + b) * (a - b)) % p
+            assert fop(hc, fid, 9, a, b, nb) == a * b % p                               # Karatsuba + reduce-only
+            assert fop(hc, fid, 10, a, b, nb) == (a * b + (a + b) * (a - b)) % p
         for a in vals[1:10]:
             assert fop(hc, fid, 4, a, 0, nb) == pow(a, -1, p)
 

@@ -461,3 +461,24 @@ def test_msm_merged_table_2p20_closed_form(dclient, oracle):
         assert m.plan_info()["merged_table"]
     finally:
         m.close()
+
+
+@pytest.mark.parametrize("mode,c_bits", [(0, 17), (0, 23), (2, 18), (2, 24)])
+def test_msm_wide_windows_small_input(dclient, oracle, mode, c_bits):
+    """Wide windows on a small input: two partition levels of the sort with (almost) empty parents, millions of
+    empty buckets in the reduction, plain table (mode 0) and window-merged table (mode 2)."""
+    c = CURVE_BY_NAME["BLS12_381"]
+    n = 5000
+    pts, p0, q = chain_points(c, n, seed=300 + c_bits)
+    m = MSMClient.new(MSMInit(PointMemoryType.HBM, False, Curve.BLS381), dclient)
+    try:
+        m.set_precompute(mode)
+        m.set_window_bits(c_bits)
+        params = MSMParams(n, (0, 0))
+        m.load_data_to_hbm(pts, 0, 0)
+        sc = random_scalars(c, n, seed=301)
+        assert run_hbm(m, params, sc) == oracle.chain_expected("BLS12_381", p0, q, sc, n)
+        plan = m.plan_info()
+        assert plan["c"] == c_bits and plan["merged_table"] == (mode == 2), plan
+    finally:
+        m.close()
