@@ -179,11 +179,12 @@ def ntt_section(args, bz, torch, dist, dc, rank, world, local):
             if i >= 2:
                 walls.append(time.perf_counter() - t0)
         tm = t.times()
+        pl = t.plan()
         v = torch.tensor([sum(walls) / len(walls), tm["step1_ms"], tm["step3_ms"]], dtype=torch.float64, device="cuda")
         dist.all_reduce(v, op=dist.ReduceOp.MAX)
         ms_val = float(v[0]) * 1e3
-        passes = None
-        layout = ("rank g holds column slab in[j1*N2 + g*C + c] in, X[(h*T+t) + N1*k2] out (strided slabs); "
+        passes = pl["column_passes"] + pl["row_passes"]
+        layout = ("N = 2^%d x 2^%d; " % (pl["log_n1"], pl["log_n2"]) + "rank g holds column slab in[j1*N2 + g*C + c] in, X[(h*T+t) + N1*k2] out (strided slabs); "
                   "step1 %.2f ms + step3 %.2f ms device time, rest = 2 host barriers" % (float(v[1]), float(v[2])))
         t.close()
     hbm_peak, _ = peaks()

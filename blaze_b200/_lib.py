@@ -81,6 +81,7 @@ SIGNATURES = {
     "bz_ntt_dist_sync": [vp],
     "bz_ntt_dist_step3": [vp],
     "bz_ntt_dist_times": [vp, ctypes.POINTER(ctypes.c_float)],
+    "bz_ntt_dist_plan": [vp, ctypes.POINTER(ctypes.c_int32)],
     "bz_poseidon_new": [vp, i32, ctypes.POINTER(vp)],
     "bz_poseidon_free": [vp],
     "bz_poseidon_loaded_binary_parameters": [vp, u32p],

@@ -332,7 +332,18 @@ __global__ void __launch_bounds__(FINAL_THREADS) k_final(const uint2* __restrict
   const uint32_t fmask = (uint32_t)nf - 1;
   for (int k = threadIdx.x; k < nf; k += blockDim.x) cnt[k] = 0;
   __syncthreads();
-  for (uint32_t i = lo + threadIdx.x; i < hi; i += FINAL_THREADS) atomicAdd(&cnt[in[i].x & fmask], 1u);
+  // four independent loads in flight per thread, then the shared-memory atomics
+  for (uint32_t i0 = lo + threadIdx.x; i0 < hi; i0 += 4 * FINAL_THREADS) {
+    uint32_t k[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const uint32_t i = i0 + u * FINAL_THREADS;
+      k[u] = i < hi ? in[i].x : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      if (i0 + u * FINAL_THREADS < hi) atomicAdd(&cnt[k[u] & fmask], 1u);
+  }
   __syncthreads();
   // exclusive scan of <= 256 counters by warp 0 (<= 8 per lane)
   if (threadIdx.x < 32) {
@@ -357,9 +368,16 @@ __global__ void __launch_bounds__(FINAL_THREADS) k_final(const uint2* __restrict
   __syncthreads();
   const uint32_t n = hi - lo;
   if (n <= FINAL_STAGE) {
-    for (uint32_t i = lo + threadIdx.x; i < hi; i += FINAL_THREADS) {
-      uint2 e = in[i];
-      stage[atomicAdd(&cnt[e.x & fmask], 1u)] = e.y;
+    for (uint32_t i0 = lo + threadIdx.x; i0 < hi; i0 += 4 * FINAL_THREADS) {
+      uint2 e[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const uint32_t i = i0 + u * FINAL_THREADS;
+        e[u] = i < hi ? in[i] : make_uint2(0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (i0 + u * FINAL_THREADS < hi) stage[atomicAdd(&cnt[e[u].x & fmask], 1u)] = e[u].y;
     }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < n; i += FINAL_THREADS) sorted[lo + i] = stage[i];

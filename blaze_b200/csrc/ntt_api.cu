@@ -323,7 +323,17 @@ extern "C" int32_t bz_ntt_dist_new(bz_dclient* dc, int32_t field, int32_t log_si
     return bz_fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "bad rank/world %d/%d (world must be a power of two <= %d)", rank, world, NTT_MAX_PEERS);
   if (log_size > ntt_two_adicity(field) || log_size > 30) return bz_fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "log size %d unsupported", log_size);
   int lw = ilog2u(world);
+  // N = N1 x N2 = 2^l1 x 2^l2: the split with the fewest global passes (radix <= 2^9 each), e.g. 27 = 9 + 18 -> 1 + 2
+  // passes instead of 13 + 14 -> 2 + 2; ties go to the more balanced split
   int l1 = log_size / 2, l2 = log_size - l1;
+  {
+    auto passes = [](int l) { return l == 0 ? 0 : (l + 8) / 9; };
+    int best = passes(l1) + passes(l2);
+    for (int a = std::max(lw, 1); a <= log_size - std::max(lw, 1); a++) {   // both factors >= max(world, 2)
+      int b = log_size - a, np = passes(a) + passes(b);
+      if (np < best || (np == best && std::abs(a - b) < std::abs(l1 - l2))) { best = np; l1 = a; l2 = b; }
+    }
+  }
   // the last column pass needs radix >= world, and each rank at least one row / column
   if (l1 < lw || l2 < lw || l1 < 1) return bz_fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "2^%d is too small for %d ranks", log_size, world);
   bz_ntt_dist* t = new bz_ntt_dist();
@@ -544,6 +554,15 @@ extern "C" int32_t bz_ntt_dist_step3(bz_ntt_dist* t) {
     Ns *= R;
   }
   cudaEventRecord(t->ev[3], st);
+  return BZ_OK;
+}
+
+extern "C" int32_t bz_ntt_dist_plan(bz_ntt_dist* t, int32_t out[4]) {
+  if (!t || !out) return bz_fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null argument");
+  out[0] = t->l1;
+  out[1] = t->l2;
+  out[2] = (int32_t)std::max<size_t>(1, plan_radices(t->l1).size());
+  out[3] = (int32_t)plan_radices(t->l2).size();
   return BZ_OK;
 }
 

@@ -167,6 +167,11 @@ class DistributedNTT:
         check(lib().bz_ntt_dist_times(self._h, out))
         return {"step1_ms": out[0], "step3_ms": out[1]}
 
+    def plan(self):
+        out = (ctypes.c_int32 * 4)()
+        check(lib().bz_ntt_dist_plan(self._h, out))
+        return {"log_n1": out[0], "log_n2": out[1], "column_passes": out[2], "row_passes": out[3]}
+
     def buffers(self):
         a, o, n = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
         check(lib().bz_ntt_dist_buffers(self._h, ctypes.byref(a), ctypes.byref(o), ctypes.byref(n)))

@@ -184,6 +184,7 @@ int32_t bz_ntt_dist_step1(bz_ntt_dist* t);
 int32_t bz_ntt_dist_sync(bz_ntt_dist* t);   /* drains the rank's stream; the cross-rank barrier is the caller's */
 int32_t bz_ntt_dist_step3(bz_ntt_dist* t);
 int32_t bz_ntt_dist_times(bz_ntt_dist* t, float ms[2]);   /* CUDA-event ms of the last step1 / step3 */
+int32_t bz_ntt_dist_plan(bz_ntt_dist* t, int32_t out[4]);   /* log2 N1, log2 N2, column passes, row passes */
 
 /* ------------------------------------------------------------------ PoseidonClient (src/ingo_hash/poseidon_api.rs)
  * Stream of 32-byte little-endian BLS12-381 Fr elements in, 64-byte records out:

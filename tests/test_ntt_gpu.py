@@ -139,7 +139,8 @@ def test_distributed_ntt_two_ranks_if_available(oracle):
         pytest.skip("needs 2 GPUs")
     import os
     here = os.path.dirname(os.path.abspath(__file__))
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(here, "dist_ntt_check.py"), "16"],
-                       capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0 and "DIST_NTT_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    for log_n in ("16", "21"):      # 8 + 8 (one pass each) and 9 + 12 (unbalanced split: 1 + 2 passes)
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                            "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(here, "dist_ntt_check.py"), log_n],
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "DIST_NTT_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
