@@ -63,10 +63,12 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).  ONE sampler for
+    the whole job (rank 0 polls the N GPUs of the run every 500 ms): a poller per rank at 5 Hz measurably slows
+    the CUDA driver calls of all ranks at N = 8."""
 
-    def __init__(self, index):
-        self.index = index
+    def __init__(self, indices):
+        self.indices = list(indices)
         self.proc = None
         self.lines = []
 
@@ -75,8 +77,8 @@ class ClockSampler:
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", ",".join(str(i) for i in self.indices), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "500"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -89,7 +91,7 @@ class ClockSampler:
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
+        time.sleep(0.3)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         for ln in self.lines:
@@ -106,7 +108,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "gpus_sampled": len(self.indices)}
 
 
 def cpu_port_rate(log_n, threads=0, seed=900):
@@ -369,10 +371,11 @@ def main():
             raise SystemExit("bench: GPU result differs from the oracle closed form -- number is INVALID")
 
     # ---- timed region 1: device-resident (value)
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(range(world)) if rank == 0 else None
     launches0 = lib().bz_kernel_launch_count()
     barrier()
-    sampler.start()
+    if sampler:
+        sampler.start()
     t0 = time.perf_counter()
     dev_ms, acc_ms, sort_ms, red_ms = [], [], [], []
     for _ in range(args.steps):
@@ -384,7 +387,7 @@ def main():
         red_ms.append(pt["reduce"])
     barrier()
     wall = time.perf_counter() - t0
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else None
     launches = lib().bz_kernel_launch_count() - launches0
 
     # ---- timed region 2: end to end with host buffers, strictly serial calls

@@ -296,6 +296,8 @@ struct bz_msm {
   int precomp_mode = 1;
   bool precomp_failed = false;   // allocation failed for this point set: stay on the plain table
   uint64_t table_uses = 0;       // MSMs launched on the current arena table
+  uint8_t* comb_dev = nullptr;   // scratch of bz_msm_combine_results
+  size_t comb_cap = 0;
   uint8_t* dma_points = nullptr;
   size_t dma_points_cap = 0;
   // DMA mode: the points travel on the copy stream BEHIND the scalars, so digits + sort of the task run while
@@ -399,14 +401,14 @@ static int32_t make_plan(bz_msm* m, uint64_t M, int words_per_scalar, bool merge
       // one bucket set: the reduction is paid once, the table costs W * M entries of HBM
       if ((uint64_t)W * M >= (1ull << 31)) continue;   // entry index = w*M + i must leave bit 31 for the sign
       if ((size_t)W * M * m->ops->affine_bytes + ws_bytes_estimate(m, (uint64_t)W * M, c, 1) > mem_free) continue;
-      double cost = (double)W * (double)M * 1.06 + 6.0 * (double)(1ull << (c - 1));
+      double cost = (double)W * (double)M * 1.06 + 4.0 * (double)(1ull << (c - 1));
       if (cost < best) { best = cost; best_c = c; }
       continue;
     }
     // measured on B200 (perf_probe, 2^24..2^26): per (scalar, window) the sort costs about 0.06 of a mixed add;
-    // the running-sum reduction costs about 6 mixed-add equivalents per bucket
+    // the running-sum reduction costs about 4 mixed-add equivalents per bucket (11 ms for 2^23 buckets)
     double sort_w = 0.06;
-    double cost = (double)W * ((double)M * (1.0 + sort_w) + 6.0 * (double)(1ull << (c - 1)));
+    double cost = (double)W * ((double)M * (1.0 + sort_w) + 4.0 * (double)(1ull << (c - 1)));
     // a top window with only a few bits funnels all M entries into a handful of buckets of one
     // coarse bin (one CTA sorts them, long merge chains): avoid such c unless the problem is tiny
     int top_bits = sbits - c * (W - 1);
@@ -500,7 +502,7 @@ static int32_t make_plan(bz_msm* m, uint64_t M, int words_per_scalar, bool merge
   A((uint8_t**)&m->ws.part_pt, (size_t)p.nseg * 2 * xb);
   {
     uint64_t n = p.nseg, tot = 0;
-    for (int lvl = 0;; lvl++) { const uint64_t g = merge_group(lvl); n = (n + g - 1) / g; tot += n; if (n == 1) break; }
+    for (int lvl = 0;; lvl++) { const uint64_t g = merge_group(lvl, p.nseg); n = (n + g - 1) / g; tot += n; if (n == 1) break; }
     A(&m->ws.part2_id, (size_t)tot * 2 * 4);
     A((uint8_t**)&m->ws.part2_pt, (size_t)tot * 2 * xb);
   }
@@ -581,6 +583,7 @@ extern "C" int32_t bz_msm_free(bz_msm* m) {
   if (m->table) cudaFree(m->table);
   wtable_free(m);
   if (m->dma_points) cudaFree(m->dma_points);
+  if (m->comb_dev) cudaFree(m->comb_dev);
   for (int b = 0; b < 2; b++) {
     if (m->scalars_dev[b]) cudaFree(m->scalars_dev[b]);
     if (m->ev_copied[b]) cudaEventDestroy(m->ev_copied[b]);
@@ -1005,14 +1008,20 @@ extern "C" int32_t bz_msm_combine_results(bz_msm* m, const uint8_t* records, int
   if (rc) return rc;
   size_t rs = 3 * (size_t)m->ops->fq_bytes;
   if (out_len < rs) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "result buffer too small");
-  uint8_t* d = nullptr;
-  CUDA_TRY(BZ_ERR_WRITE, cudaMalloc((void**)&d, rs * (n + 1)));
+  std::lock_guard<std::mutex> lk(m->mu);
+  if (m->comb_cap < rs * (n + 1)) {   // small scratch kept across calls (no cudaMalloc / cudaFree per step)
+    if (m->comb_dev) cudaFree(m->comb_dev);
+    m->comb_dev = nullptr;
+    m->comb_cap = 0;
+    CUDA_TRY(BZ_ERR_WRITE, cudaMalloc((void**)&m->comb_dev, rs * (n + 1)));
+    m->comb_cap = rs * (n + 1);
+  }
+  uint8_t* d = m->comb_dev;
   cudaStream_t st = m->dc->stream;
   cudaMemcpyAsync(d, records, rs * n, cudaMemcpyHostToDevice, st);
   m->ops->combine_results(d, n, d + rs * n, st);
   cudaMemcpyAsync(out, d + rs * n, rs, cudaMemcpyDeviceToHost, st);
   cudaError_t e = cudaStreamSynchronize(st);
-  cudaFree(d);
   if (e != cudaSuccess) return fail(BZ_ERR_UNKNOWN, "combine failed: %s", cudaGetErrorString(e));
   return BZ_OK;
 }

@@ -468,18 +468,21 @@ __global__ void __launch_bounds__(128) k_merge_level(const uint32_t* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------
-// bucket reduction.  Per window we need T = sum_i i * A[i] over the bucket array A[0..n) (bucket 0
-// has weight 0, so it needs no special case).  Chunks of s entries:
-//     T = sum_k R_k + s * sum_k k * S_k,   R_k = sum_{t<s} t * A[ks+t],  S_k = sum_{t<s} A[ks+t]
-// and the second term is the same problem on the array S (one entry per chunk): a recursion of
-// log_s(n) levels, one launch each, every level with thousands of independent running sums.
-// The level results are folded as they go:  V^l_k = s^l * R^l_k + sum_{j in chunk k} V^{l-1}_j,
+// bucket reduction.  Slot i of the bucket array holds the bucket of VALUE i + 1 (zero digits never reach the
+// sort), so per window we need T = sum_i (i+1) A[i].  Chunks of s entries:
+//     T = sum_k R_k + s * sum_k k * S_k,   R_k = sum_{t<s} (t+1) * A[ks+t],  S_k = sum_{t<s} A[ks+t]
+// and the second term is the plain weighted sum (weights k = 0, 1, ...) of the array s * S_k (one entry per
+// chunk): a recursion of log_s(n) levels, one launch each, every level with thousands of independent running
+// sums.  Every level hands the NEXT level its chunk sums already multiplied by its own chunk size (log2 s
+// doublings per thread), so the weighted sums R need no rescaling, and the level results are folded as they go:
+//     V^l_k = R^l_k + sum_{j in chunk k} V^{l-1}_j
 // so the window total is the single V of the top level.
 template <class C>
 __global__ void __launch_bounds__(128, 2)
 k_reduce_level(const XyzzM<C>* __restrict__ A, const XyzzM<C>* __restrict__ Vin, uint32_t n, uint32_t a_stride,
                int cbits /* >= 0: entry i lives in slot (i & (2^cbits - 1)) * nfine + (i >> cbits) */, uint32_t nfine,
-               uint32_t s, uint32_t nchunks, int W, int level_shift /* l * log2(s) */,
+               uint32_t s, uint32_t nchunks, int W, int first /* level 0: weights t+1 instead of t */,
+               int out_shift /* log2(s), 0 at the top level: Sout = 2^out_shift * chunk sum */,
                XyzzM<C>* __restrict__ Sout, XyzzM<C>* __restrict__ Vout) {
   typedef dev<C> D;
   typedef ec<C> G;
@@ -501,7 +504,7 @@ k_reduce_level(const XyzzM<C>* __restrict__ A, const XyzzM<C>* __restrict__ Vin,
     XYZZ<C> v = D::load_xyzz(a + slot(lo));
     G::add(S, v);
   }
-  for (int d = 0; d < level_shift; d++) R = G::dbl(R);
+  if (first) G::add(R, S);
   if (Vin) {
     const XyzzM<C>* vin = Vin + (uint64_t)w * n;
     for (uint32_t i = lo; i < hi; i++) {
@@ -509,25 +512,21 @@ k_reduce_level(const XyzzM<C>* __restrict__ A, const XyzzM<C>* __restrict__ Vin,
       G::add(R, v);
     }
   }
-  D::store_xyzz(Sout + t, S);
   D::store_xyzz(Vout + t, R);
+  for (int d = 0; d < out_shift; d++) S = G::dbl(S);
+  D::store_xyzz(Sout + t, S);
 }
 
 // Horner over the window sums, normalise, serialise
-// Slot i of the bucket array holds the bucket of VALUE i + 1 (zero digits never reach the sort), so the window
-// sum is  sum_i (i+1) A[i] = V + S  with V = sum_i i A[i] and S = sum_i A[i], the two top-level outputs.
 template <class C>
-__global__ void k_finish(const XyzzM<C>* __restrict__ winV, const XyzzM<C>* __restrict__ winS, int W, int c,
-                         uint8_t* __restrict__ result) {
+__global__ void k_finish(const XyzzM<C>* __restrict__ win, int W, int c, uint8_t* __restrict__ result) {
   typedef dev<C> D;
   typedef ec<C> G;
   if (blockIdx.x || threadIdx.x) return;
-  XYZZ<C> acc = G::infinity();
-  for (int w = W - 1; w >= 0; w--) {
-    if (w != W - 1) for (int d = 0; d < c; d++) acc = G::dbl(acc);
-    XYZZ<C> v = D::load_xyzz(winV + w);
-    G::add(acc, v);
-    v = D::load_xyzz(winS + w);
+  XYZZ<C> acc = D::load_xyzz(win + (W - 1));
+  for (int w = W - 2; w >= 0; w--) {
+    for (int d = 0; d < c; d++) acc = G::dbl(acc);
+    XYZZ<C> v = D::load_xyzz(win + w);
     G::add(acc, v);
   }
   D::store_result(result, acc);
@@ -650,7 +649,7 @@ struct CurveLaunch {
       XyzzM<C>* out_pt = (XyzzM<C>*)ws.part2_pt;
       uint64_t n_children = p.nseg, child_span = p.seg_len;
       for (int level = 0;; level++) {
-        const uint32_t group = merge_group(level);
+        const uint32_t group = merge_group(level, p.nseg);
         const uint64_t span = child_span * group;   // sorted positions covered by one group
         uint64_t n_groups = (n_children + group - 1) / group;
         k_merge_level<C><<<(unsigned)((n_groups + 127) / 128), 128, 0, st>>>(ws.goff, ngoff, buckets, in_id, in_pt,
@@ -676,9 +675,8 @@ struct CurveLaunch {
     uint32_t n = p.nvalues, a_stride = p.nb;
     int perm_bits = p.rest;   // level 0 reads value i at its sort slot (i mod 2^rest) * 2^fb + (i >> rest)
     XyzzM<C>* scratch[2] = {(XyzzM<C>*)ws.red_a, (XyzzM<C>*)ws.red_b};
-    int level = 0, shift = 0;
+    int level = 0;
     const XyzzM<C>* top = nullptr;
-    const XyzzM<C>* topS = nullptr;
     while (true) {
       const uint32_t s = level == 0 ? p.chunk : 4;
       int log_s = 0;
@@ -687,21 +685,19 @@ struct CurveLaunch {
       XyzzM<C>* Sout = scratch[level & 1];
       XyzzM<C>* Vout = Sout + (size_t)p.W * nch;
       uint32_t nt = (uint32_t)p.W * nch;
-      k_reduce_level<C><<<(nt + 127) / 128, 128, 0, st>>>(A, Vin, n, a_stride, perm_bits, 1u << p.fb, s, nch, p.W, shift, Sout,
-                                                        Vout);
+      k_reduce_level<C><<<(nt + 127) / 128, 128, 0, st>>>(A, Vin, n, a_stride, perm_bits, 1u << p.fb, s, nch, p.W,
+                                                        level == 0 ? 1 : 0, nch == 1 ? 0 : log_s, Sout, Vout);
       g_kernel_launches += 1;
       top = Vout;
-      topS = Sout;
       if (nch == 1) break;
       A = Sout;
       Vin = Vout;
       n = nch;
       a_stride = nch;
       perm_bits = -1;
-      shift += log_s;
       level++;
     }
-    k_finish<C><<<1, 32, 0, st>>>(top, topS, p.W, p.c, ws.result);
+    k_finish<C><<<1, 32, 0, st>>>(top, p.W, p.c, ws.result);
   }
   static void build_wtable(void* wtable, uint64_t n, int levels, int c, cudaStream_t st) {
     constexpr int K = 16;

@@ -18,11 +18,16 @@ enum : int {
   BZ_ERR_SCALAR_RANGE = 1,   // a scalar was not canonical (>= r) / top digit overflow
 };
 
-// children per thread in the partial-merge tree: 64 at the first level (millions of segments: throughput), 8 above
-// (a level costs about `group` sequential additions of latency whatever its size, and the upper levels are tiny)
+// children per thread in the partial-merge tree.  A level costs about `group` sequential additions of latency
+// whatever its size: 64 at the first level only when that still fills the machine (millions of segments), else 16;
+// 8 above (the upper levels are tiny).
 #define MERGE_GROUP 64
+#define MERGE_GROUP_SMALL 16
 #define MERGE_GROUP_UPPER 8
-static inline unsigned merge_group(int level) { return level == 0 ? MERGE_GROUP : MERGE_GROUP_UPPER; }
+static inline unsigned merge_group(int level, unsigned long long nseg) {
+  if (level > 0) return MERGE_GROUP_UPPER;
+  return nseg / MERGE_GROUP >= 148ull * 384 ? MERGE_GROUP : MERGE_GROUP_SMALL;
+}
 
 struct DigitConst {
   uint32_t K[9];      // sum of the half-window offsets (see k_digits)

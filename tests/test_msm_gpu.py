@@ -482,3 +482,20 @@ def test_msm_wide_windows_small_input(dclient, oracle, mode, c_bits):
         assert plan["c"] == c_bits and plan["merged_table"] == (mode == 2), plan
     finally:
         m.close()
+
+
+@pytest.mark.parametrize("n", [1, 2, 33])
+def test_msm_merged_table_tiny_inputs(dclient, oracle, n):
+    c = CURVE_BY_NAME["BN254"]
+    pts, _, _ = chain_points(c, n, seed=400 + n)
+    m = MSMClient.new(MSMInit(PointMemoryType.HBM, False, Curve.BN254), dclient)
+    try:
+        m.set_precompute(2)
+        params = MSMParams(n, (0x40, 0))
+        m.load_data_to_hbm(pts, 0x40, 0)
+        for it in range(2):
+            sc = random_scalars(c, n, seed=410 + it)
+            assert run_hbm(m, params, sc) == oracle.msm_naive("BN254", bytes(pts), bytes(sc), n, 1)
+        assert m.plan_info()["merged_table"]
+    finally:
+        m.close()
