@@ -157,6 +157,44 @@ def ntt_section(args, bz, torch, dist, dc, rank, world, local):
             if i >= 2:
                 ms.append(t.phase_times()["total"])
         passes = t.phase_times()["passes"]
+        # end to end through the client calls with pinned HOST buffers (4 GiB in + 4 GiB out per transform at 2^27):
+        # serial = set_data -> start_process -> wait_result -> result; pipelined = the reference's double-buffer cycle
+        # (integration_ntt.rs:103-136) from one host thread: the transform of slot 1-h runs while slot h is read out
+        # and refilled
+        e2e = None
+        try:
+            hin = torch.empty(n * 32, dtype=torch.uint8).pin_memory()
+            hout = torch.empty(n * 32, dtype=torch.uint8).pin_memory()
+            hin.copy_(view)
+            bi, bo = (hin.data_ptr(), n * 32), (hout.data_ptr(), n * 32)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(2):
+                t.set_data(bz.NTTInput(0, bi))
+                t.start_process(0)
+                t.wait_result()
+                t.result(0, out=bo)
+            serial_ms = 1e3 * (time.perf_counter() - t0) / 2
+            k = 4
+            t.set_data(bz.NTTInput(0, bi))
+            t.start_process(0)
+            t.set_data(bz.NTTInput(1, bi))
+            t.wait_result()
+            h = 0
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(k):
+                t.start_process(1 - h)
+                t.result(h, out=bo)
+                t.set_data(bz.NTTInput(h, bi))
+                t.wait_result()
+                h = 1 - h
+            pipe_ms = 1e3 * (time.perf_counter() - t0) / k
+            e2e = {"serial_ms": serial_ms, "pipelined_ms": pipe_ms, "h2d_bytes": n * 32, "d2h_bytes": n * 32,
+                   "note": "PCIe bound: 2 x %.1f GiB per transform; one host thread, so H2D and D2H do not overlap each other" % (n * 32 / 2**30)}
+            del hin, hout
+        except Exception as ex:
+            e2e = {"error": repr(ex)}
         t.close()
         ms_val = sum(ms) / len(ms)
         layout = "natural order in / natural order out, in place in slot 0"
@@ -193,6 +231,7 @@ def ntt_section(args, bz, torch, dist, dc, rank, world, local):
     npass = passes if passes else 4
     gbs = npass * 2 * n * 32 / world / (ms_val / 1e3) / 1e9
     return {"metric": "2^%d NTT over BLS12-381 Fr, ms" % log_n, "ms": ms_val, "n_gpus": world, "passes": npass,
+            "e2e": e2e if world == 1 else None,
             "layout": layout, "semantics": "arkworks Radix2EvaluationDomain::fft (natural in/out), forward",
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s per GPU", "frac": gbs / hbm_peak,
                          "algorithmic_bytes": npass * 2 * n * 32}}

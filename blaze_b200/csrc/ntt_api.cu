@@ -40,6 +40,12 @@ struct bz_ntt {
   cudaEvent_t done = nullptr;
   bool launched = false;
   float last_ms = 0;
+  // Copies run on their own streams so that the H2D of one slot and the D2H of the other overlap the transform
+  // (the reference's double-buffer pipeline, integration_ntt.rs:103-136).  Per slot: input landed / transform
+  // finished / output read -- each stream waits only for what it needs.
+  cudaStream_t h2d = nullptr, d2h = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_cmp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+  bool in_valid[2] = {false, false}, cmp_valid[2] = {false, false}, out_valid[2] = {false, false};
   std::mutex mu;
 };
 
@@ -54,11 +60,14 @@ static std::vector<int> plan_radices(int log_n) {
 static NttPassParams ntt_pass_params(bz_ntt* t, size_t p, uint64_t Ns);
 
 static int32_t ntt_alloc_slot(bz_ntt* t, int s) {
+  bool fresh = false;
   for (int k = 0; k < 2; k++)
     if (!t->buf[s][k]) {
       CUDA_TRY(BZ_ERR_WRITE, cudaMalloc((void**)&t->buf[s][k], std::max<uint64_t>(t->n, 1) * 32));
       CUDA_TRY(BZ_ERR_WRITE, cudaMemsetAsync(t->buf[s][k], 0, std::max<uint64_t>(t->n, 1) * 32, dc_stream(t->dc)));
+      fresh = true;
     }
+  if (fresh) CUDA_TRY(BZ_ERR_WRITE, cudaStreamSynchronize(dc_stream(t->dc)));   // zero fill before any copy stream touches it
   return BZ_OK;
 }
 
@@ -80,6 +89,13 @@ static int32_t ntt_new_common(bz_dclient* dc, int field, int log_n, int inverse,
   cudaEventCreate(&t->ev[0]);
   cudaEventCreate(&t->ev[1]);
   cudaEventCreateWithFlags(&t->done, cudaEventBlockingSync | cudaEventDisableTiming);
+  cudaStreamCreateWithFlags(&t->h2d, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&t->d2h, cudaStreamNonBlocking);
+  for (int s = 0; s < 2; s++) {
+    cudaEventCreateWithFlags(&t->ev_in[s], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&t->ev_cmp[s], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&t->ev_out[s], cudaEventDisableTiming);
+  }
   *out = t;
   return BZ_OK;
 }
@@ -96,6 +112,10 @@ extern "C" int32_t bz_ntt_free(bz_ntt* t) {
   if (!t) return BZ_OK;
   cudaSetDevice(dc_device(t->dc));
   cudaStreamSynchronize(dc_stream(t->dc));
+  if (t->h2d) { cudaStreamSynchronize(t->h2d); cudaStreamDestroy(t->h2d); }
+  if (t->d2h) { cudaStreamSynchronize(t->d2h); cudaStreamDestroy(t->d2h); }
+  for (int s = 0; s < 2; s++)
+    for (cudaEvent_t e : {t->ev_in[s], t->ev_cmp[s], t->ev_out[s]}) if (e) cudaEventDestroy(e);
   for (auto& s : t->buf) for (auto& b : s) if (b) cudaFree(b);
   if (t->tab_mem) cudaFree(t->tab_mem);
   for (auto p : t->tw_full) if (p) cudaFree(p);
@@ -165,9 +185,14 @@ extern "C" int32_t bz_ntt_set_data(bz_ntt* t, size_t buf_host, const uint8_t* da
   std::lock_guard<std::mutex> lk(t->mu);
   rc = ntt_alloc_slot(t, (int)buf_host);
   if (rc) return rc;
-  cudaStream_t st = dc_stream(t->dc);
+  // the slot must be idle: its last transform finished, its last result read out (stream-side waits only)
+  cudaStream_t st = t->h2d;
+  if (t->cmp_valid[buf_host]) CUDA_TRY(BZ_ERR_WRITE, cudaStreamWaitEvent(st, t->ev_cmp[buf_host], 0));
+  if (t->out_valid[buf_host]) CUDA_TRY(BZ_ERR_WRITE, cudaStreamWaitEvent(st, t->ev_out[buf_host], 0));
   CUDA_TRY(BZ_ERR_WRITE, cudaMemcpyAsync(t->buf[buf_host][t->cur[buf_host]], data, len, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(BZ_ERR_WRITE, cudaStreamSynchronize(st));   // caller may drop `data` (move-in semantics)
+  CUDA_TRY(BZ_ERR_WRITE, cudaEventRecord(t->ev_in[buf_host], st));
+  t->in_valid[buf_host] = true;
+  CUDA_TRY(BZ_ERR_WRITE, cudaStreamSynchronize(st));   // caller may drop `data` (move-in semantics); the work stream keeps running
   return BZ_OK;
 }
 
@@ -207,6 +232,8 @@ static NttPassParams ntt_pass_params(bz_ntt* t, size_t p, uint64_t Ns) {
 static int32_t ntt_enqueue(bz_ntt* t, int s) {
   cudaStream_t st = dc_stream(t->dc);
   uint64_t Ns = 1;
+  if (t->in_valid[s]) cudaStreamWaitEvent(st, t->ev_in[s], 0);     // the slot's input has landed
+  if (t->out_valid[s]) cudaStreamWaitEvent(st, t->ev_out[s], 0);   // nobody is still reading the slot out
   cudaEventRecord(t->ev[0], st);
   for (size_t p = 0; p < t->radices.size(); p++) {
     NttPassParams P = ntt_pass_params(t, p, Ns);
@@ -220,6 +247,8 @@ static int32_t ntt_enqueue(bz_ntt* t, int s) {
   }
   cudaEventRecord(t->ev[1], st);
   cudaEventRecord(t->done, st);
+  cudaEventRecord(t->ev_cmp[s], st);
+  t->cmp_valid[s] = true;
   t->launched = true;
   return BZ_OK;
 }
@@ -260,9 +289,13 @@ extern "C" int32_t bz_ntt_result(bz_ntt* t, size_t buf_num, uint8_t* out, size_t
   std::lock_guard<std::mutex> lk(t->mu);
   rc = ntt_alloc_slot(t, (int)buf_num);
   if (rc) return rc;
-  cudaStream_t st = dc_stream(t->dc);
+  cudaStream_t st = t->d2h;
+  if (t->cmp_valid[buf_num]) CUDA_TRY(BZ_ERR_READ, cudaStreamWaitEvent(st, t->ev_cmp[buf_num], 0));
+  if (t->in_valid[buf_num]) CUDA_TRY(BZ_ERR_READ, cudaStreamWaitEvent(st, t->ev_in[buf_num], 0));
   CUDA_TRY(BZ_ERR_READ, cudaMemcpyAsync(out, t->buf[buf_num][t->cur[buf_num]], t->n * 32, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(BZ_ERR_READ, cudaStreamSynchronize(st));
+  CUDA_TRY(BZ_ERR_READ, cudaEventRecord(t->ev_out[buf_num], st));
+  t->out_valid[buf_num] = true;
+  CUDA_TRY(BZ_ERR_READ, cudaStreamSynchronize(st));   // blocks the host on this copy only
   return BZ_OK;
 }
 
@@ -281,6 +314,8 @@ extern "C" int32_t bz_ntt_slot_device_ptr(bz_ntt* t, size_t buf_num, uint64_t* d
   rc = ntt_alloc_slot(t, (int)buf_num);
   if (rc) return rc;
   CUDA_TRY(BZ_ERR_UNKNOWN, cudaStreamSynchronize(dc_stream(t->dc)));
+  CUDA_TRY(BZ_ERR_UNKNOWN, cudaStreamSynchronize(t->h2d));
+  CUDA_TRY(BZ_ERR_UNKNOWN, cudaStreamSynchronize(t->d2h));
   *dev_ptr = (uint64_t)(uintptr_t)t->buf[buf_num][t->cur[buf_num]];
   return BZ_OK;
 }

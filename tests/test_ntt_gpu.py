@@ -91,6 +91,41 @@ def test_ntt_double_buffer_pipeline(dclient, oracle):
         t.close()
 
 
+def test_ntt_pipeline_reference_order_overlapped_copies(dclient, oracle):
+    """The reference's own pipelined cycle (integration_ntt.rs:103-136) at a size where the copies take as long
+    as the transform: start_process(1-h); result(h); set_data(h); wait_result().  The copies run on their own
+    streams here, so every ordering hazard (read-out vs next transform, refill vs read-out) is exercised."""
+    name, log_n = "BLS12_381", 20
+    n = 1 << log_n
+    t = NTTClient.new_ex(dclient, FIELDS[name], log_n)
+    try:
+        rounds = 6
+        ins = [rand_elems(name, n, seed=500 + i) for i in range(rounds)]
+        exps = []
+        for d in ins:
+            e = d.copy()
+            oracle.ntt(name, e, log_n)
+            exps.append(bytes(e))
+        t.initialize(NttInit())
+        outs = []
+        h = 0
+        t.set_data(NTTInput(0, ins[0]))
+        t.start_process(0)
+        t.set_data(NTTInput(1, ins[1]))
+        t.wait_result()
+        for i in range(1, rounds):
+            t.start_process(1 - h)                       # transform input i on the other slot
+            outs.append(bytes(t.result(h)))              # read output i-1 meanwhile
+            if i + 1 < rounds:
+                t.set_data(NTTInput(h, ins[i + 1]))      # refill the slot just read
+            t.wait_result()
+            h = 1 - h
+        outs.append(bytes(t.result(h)))
+        assert outs == exps
+    finally:
+        t.close()
+
+
 def test_ntt_reference_constructor_is_2p27(dclient):
     t = NTTClient.new(NTT.Ntt, dclient)
     try:
