@@ -261,11 +261,9 @@ static cudaError_t launch_pass_t(const NttPassParams& Pin, cudaStream_t st) {
   P.lv = 0;
   while ((1 << P.lv) < V) P.lv++;
   size_t smem = ((size_t)2 * R * V + 2 * R) * sizeof(uint4);
-  static size_t configured = 0;
-  if (smem > configured) {
+  {   // per device and cheap: set on every launch (a process may drive several devices)
     cudaError_t e = cudaFuncSetAttribute(k_ntt_pass<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = smem;
   }
   uint64_t ctas = (P.Q + V - 1) / V;
   k_ntt_pass<F><<<(unsigned)ctas, 256, smem, st>>>(P);
