@@ -463,7 +463,7 @@ def test_msm_merged_table_2p20_closed_form(dclient, oracle):
         m.close()
 
 
-@pytest.mark.parametrize("mode,c_bits", [(0, 17), (0, 23), (2, 18), (2, 24)])
+@pytest.mark.parametrize("mode,c_bits", [(0, 17), (0, 23), (2, 18), (2, 24), (2, 26)])   # 26: three partition levels
 def test_msm_wide_windows_small_input(dclient, oracle, mode, c_bits):
     """Wide windows on a small input: two partition levels of the sort with (almost) empty parents, millions of
     empty buckets in the reduction, plain table (mode 0) and window-merged table (mode 2)."""
