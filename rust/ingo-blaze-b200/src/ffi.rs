@@ -36,6 +36,7 @@ extern "C" {
     pub fn bz_msm_load_data_to_hbm(m: *mut bz_msm, points: *const u8, len: usize, addr: u64, offset: u64) -> i32;
     pub fn bz_msm_get_data_from_hbm(m: *mut bz_msm, out: *mut u8, len: usize, addr: u64, offset: u64) -> i32;
     pub fn bz_msm_sizes(m: *mut bz_msm, scalar: *mut u32, point: *mut u32, result: *mut u32, factor: *mut u32) -> i32;
+    pub fn bz_msm_set_precompute(m: *mut bz_msm, mode: i32) -> i32;
 
     pub fn bz_ntt_new(dc: *mut bz_dclient, ntt_type: i32, out: *mut *mut bz_ntt) -> i32;
     pub fn bz_ntt_free(t: *mut bz_ntt) -> i32;

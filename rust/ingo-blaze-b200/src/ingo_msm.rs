@@ -67,6 +67,9 @@ impl MSMClient {
         check(unsafe { ffi::bz_msm_get_data_from_hbm(self.h, res.as_mut_ptr(), data_len, addr, offset) })?;
         Ok(res)
     }
+    /// B200 addition: 0 = never, 1 = on reuse (default), 2 = always derive the table of window multiples
+    /// (2^(c w) P) from an HBM-resident point set so that all windows share one bucket set.
+    pub fn set_precompute(&self, mode: i32) -> Result<()> { check(unsafe { ffi::bz_msm_set_precompute(self.h, mode) }) }
     pub fn get_api(&self) {}
 }
 impl Drop for MSMClient { fn drop(&mut self) { unsafe { ffi::bz_msm_free(self.h); } } }
