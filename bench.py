@@ -17,6 +17,10 @@ Multi-GPU (torchrun, one rank per GPU): the MSM is point-sharded (rank g owns po
 [g N/G, (g+1) N/G)), no data-path collective; the only exchange is an all-gather of the G 144-byte
 partial results, summed by bz_msm_combine_results.  scaling = "strong" (total work fixed at 2^26).
 
+Secondary sections of the same JSON line (N = 1 only unless noted): `ntt` (2^27 NTT ms, device-resident; also at
+N > 1 as the four-step across the ranks; `ntt.e2e` = through the client calls with pinned host buffers), `dma_mode`
+(BASELINE.json configs[2]: BN254 2^24 with points AND scalars streamed from host memory every call).
+
 `--impl reference` times the reference's CPU definition of the path (the oracle port: the reference
 itself is Rust + an FPGA bitstream and cannot run here) on the host cores, same metric and config.
 """
