@@ -1,4 +1,6 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 O=gpurun_out
-(time timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 5 --warmup 3) > $O/s23_bench8.log 2>&1; tail -2 $O/s23_bench8.log | cut -c1-300
+export PROBE_CHECK=1 BZ_MSM_PRECOMP=2 PROBE_CURVE=BN254
+timeout 300 python scripts/perf_probe.py 24 0 2>&1 | grep logn | cut -c1-330
+BLAZE_B200_LIB=$PWD/blaze_b200/libblaze_b200_n8.so timeout 300 python scripts/perf_probe.py 24 0 2>&1 | grep logn | cut -c1-330

@@ -14,7 +14,9 @@ from oracle import capi
 from oracle.py import curves
 from util import random_scalars, seed_points
 
-c = curves.BLS12_381
+CNAME = os.environ.get("PROBE_CURVE", "BLS12_381")
+c = curves.CURVES[CNAME]
+CENUM = {"BLS12_381": bz.Curve.BLS381, "BLS12_377": bz.Curve.BLS377, "BN254": bz.Curve.BN254}[CNAME]
 sizes = [int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "20,22").split(",")]
 cs = [int(x) for x in (sys.argv[2] if len(sys.argv) > 2 else "0").split(",")]
 check = os.environ.get("PROBE_CHECK", "1") == "1"
@@ -23,13 +25,13 @@ print(dc.device_info(), flush=True)
 out = []
 for logn in sizes:
     n = 1 << logn
-    m = bz.MSMClient.new(bz.MSMInit(bz.PointMemoryType.HBM, False, bz.Curve.BLS381), dc)
+    m = bz.MSMClient.new(bz.MSMInit(bz.PointMemoryType.HBM, False, CENUM), dc)
     p0, q = seed_points(c, 71)
     t = time.time()
     m.generate_chain_points(p0 + q, 0, n, 0, 0)
     tg = time.time() - t
     sc = random_scalars(c, n, seed=72)
-    exp = capi.chain_expected("BLS12_381", p0, q, sc, n) if check else None
+    exp = capi.chain_expected(CNAME, p0, q, sc, n) if check else None
     params = bz.MSMParams(n, (0, 0))
     for cb in cs:
         m.set_window_bits(cb)
