@@ -1,6 +1,5 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 O=gpurun_out
-export PROBE_CHECK=1 BZ_MSM_PRECOMP=2 PROBE_CURVE=BN254
-timeout 300 python scripts/perf_probe.py 24 0 2>&1 | grep logn | cut -c1-330
-BLAZE_B200_LIB=$PWD/blaze_b200/libblaze_b200_n8.so timeout 300 python scripts/perf_probe.py 24 0 2>&1 | grep logn | cut -c1-330
+(time timeout 900 python -m pytest tests -m gpu -x -q) > $O/s24_tests.log 2>&1; tail -3 $O/s24_tests.log
+(time timeout 900 python bench.py) > $O/s24_bench.log 2>&1; tail -2 $O/s24_bench.log | cut -c1-200
