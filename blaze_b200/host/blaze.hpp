@@ -1,12 +1,15 @@
 // blaze.hpp -- header-only C++ mirror of the reference's Rust surface over the C ABI
 // (include/blaze_b200.h).  Same names, argument meaning and error behaviour as
-// /root/reference/src/{driver_client/dclient.rs, ingo_msm/msm_api.rs, ingo_ntt/ntt_api.rs, error.rs};
+// /root/reference/src/{driver_client/dclient.rs, ingo_msm/msm_api.rs, ingo_ntt/ntt_api.rs, ingo_hash/poseidon_api.rs,
+// ingo_hash/utils.rs, error.rs};
 // `Result<T>` becomes "returns T or throws DriverClientError".
 #pragma once
 #include <cstdint>
+#include <cstring>
 #include <optional>
 #include <stdexcept>
 #include <string>
+#include <algorithm>
 #include <utility>
 #include <vector>
 
@@ -103,6 +106,27 @@ class MSMClient {   // impl DriverPrimitive<MSMInit, MSMParams, MSMInput, MSMRes
     check(bz_msm_get_data_from_hbm(h_, v.data(), len, addr, off));
     return v;
   }
+  // ---- B200 additions (all optional)
+  struct PhaseTimes { float total, sort, accumulate, reduce; };
+  PhaseTimes phase_times() { float v[4]; check(bz_msm_phase_times(h_, v)); return {v[0], v[1], v[2], v[3]}; }
+  struct PlanInfo { uint32_t c, windows, buckets_per_set, segment, bucket_sets; bool merged_table; uint32_t merged_table_mib; };
+  PlanInfo plan_info() { uint32_t v[8]; check(bz_msm_plan_info_ex(h_, v)); return {v[0], v[1], v[2], v[3], v[4], v[5] != 0, v[6]}; }
+  void set_window_bits(int c) { check(bz_msm_set_window_bits(h_, c)); }
+  // 0 never / 1 on reuse (default) / 2 always: table of window multiples for an HBM-resident point set
+  void set_precompute(int mode) { check(bz_msm_set_precompute(h_, mode)); }
+  void set_scalars_device(uint64_t dev_ptr, const MSMParams& p) {
+    const auto& a = p.hbm_point_addr;
+    check(bz_msm_set_scalars_device(h_, dev_ptr, p.nof_elements, a.has_value(), a ? a->first : 0, a ? a->second : 0));
+  }
+  std::vector<uint8_t> combine_results(const std::vector<uint8_t>& records, int n) {
+    std::vector<uint8_t> out(result_point_size_);
+    check(bz_msm_combine_results(h_, records.data(), n, out.data(), out.size()));
+    return out;
+  }
+  void generate_chain_points(const std::vector<uint8_t>& p0q, uint64_t first, uint64_t n, uint64_t addr, uint64_t off) {
+    check(bz_msm_generate_chain_points(h_, p0q.data(), p0q.size(), first, n, addr, off));
+  }
+  uint32_t result_point_size() const { return result_point_size_; }
   DriverClient driver_client;   // pub field in the reference (msm_api.rs:13)
 
  private:
@@ -117,6 +141,10 @@ struct NTTInput { size_t buf_host; std::vector<uint8_t> data; };
 class NTTClient {
  public:
   NTTClient(NTT t, DriverClient dclient) : driver_client(std::move(dclient)) { check(bz_ntt_new(driver_client.raw(), (int32_t)t, &h_)); }
+  // B200 addition: any size / scalar field / direction
+  NTTClient(DriverClient dclient, Curve field, int log_size, bool inverse) : driver_client(std::move(dclient)), log_size_(log_size) {
+    check(bz_ntt_new_ex(driver_client.raw(), (int32_t)field, log_size, inverse, &h_));
+  }
   NTTClient(const NTTClient&) = delete;
   ~NTTClient() { if (h_) bz_ntt_free(h_); }
   void initialize(NttInit) { check(bz_ntt_initialize(h_)); }
@@ -128,14 +156,76 @@ class NTTClient {
   void wait_result() { check(bz_ntt_wait_result(h_)); }
   std::optional<std::vector<uint8_t>> result(std::optional<size_t> buf_num) {
     if (!buf_num) throw DriverClientError(DriverClientError::InvalidPrimitiveParam, "result(None)");
-    std::vector<uint8_t> v((size_t)1 << 32);   // 2^27 elements x 32 B
+    std::vector<uint8_t> v((size_t)32 << log_size_);   // 2^27 elements x 32 B for the reference constructor
     check(bz_ntt_result(h_, *buf_num, v.data(), v.size()));
     return v;
   }
+  float phase_ms() { float ms; uint32_t passes; check(bz_ntt_phase_times(h_, &ms, &passes)); return ms; }
   DriverClient driver_client;
 
  private:
   bz_ntt* h_ = nullptr;
+  int log_size_ = 27;
+};
+
+// ---- ingo_hash: utils.rs:2-30, poseidon_api.rs:11-253
+inline uint32_t num_of_elements_oct_tree(uint32_t tree_height) {        // utils.rs:2-10
+  uint32_t n = 0, layer = 1;
+  for (uint32_t i = 0; i < tree_height; i++) { n += layer; layer *= 8; }
+  return n;
+}
+inline uint32_t num_of_elements_in_base_layer(uint32_t tree_height) {   // utils.rs:12-14
+  uint32_t layer = 1;
+  for (uint32_t i = 1; i < tree_height; i++) layer *= 8;
+  return layer;
+}
+enum class TreeMode { TreeC = 0, TreeD = 1 };                            // utils.rs:16-30
+enum class Hash { Poseidon = 0 };                                        // poseidon_api.rs:11-13
+struct PoseidonInitializeParameters { uint32_t tree_height; TreeMode tree_mode; std::string instruction_path; };   // :19-24
+struct PoseidonResult {                                                  // :26-30
+  std::vector<uint8_t> hash_byte;
+  uint32_t hash_id, layer_id;
+  // 64-byte records: hash[32] || meta[32]; hash_id = LE32(meta[0..4]) & 0x3fffffff, layer_id = LE32(meta[3..5],0,0) >> 6  (:42-71)
+  static std::vector<PoseidonResult> parse_poseidon_hash_results(const std::vector<uint8_t>& data) {
+    std::vector<PoseidonResult> out;
+    for (size_t i = 0; i + 64 <= data.size(); i += 64) {
+      const uint8_t* el = data.data() + i;
+      uint32_t id, ly = (uint32_t)el[35] | ((uint32_t)el[36] << 8);
+      memcpy(&id, el + 32, 4);
+      out.push_back({std::vector<uint8_t>(el, el + 32), id & 0x3fffffffu, ly >> 6});
+    }
+    return out;
+  }
+};
+class PoseidonClient {   // impl DriverPrimitive<Hash, PoseidonInitializeParameters, &[u8], Vec<PoseidonResult>>, :74-146
+ public:
+  PoseidonClient(Hash t, DriverClient dclient) : dclient(std::move(dclient)) { check(bz_poseidon_new(this->dclient.raw(), (int32_t)t, &h_)); }
+  PoseidonClient(const PoseidonClient&) = delete;
+  ~PoseidonClient() { if (h_) bz_poseidon_free(h_); }
+  std::vector<uint32_t> loaded_binary_parameters() { uint32_t v[2]; check(bz_poseidon_loaded_binary_parameters(h_, v)); return {v[0], v[1]}; }
+  void initialize(const PoseidonInitializeParameters& p) {
+    check(bz_poseidon_initialize(h_, p.tree_height, (int32_t)p.tree_mode, p.instruction_path.c_str()));
+  }
+  void set_data(const uint8_t* input, size_t len) { check(bz_poseidon_set_data(h_, input, len)); }
+  void set_data(const std::vector<uint8_t>& input) { set_data(input.data(), input.size()); }
+  void start_process(std::optional<size_t> = std::nullopt) { check(bz_poseidon_start_process(h_)); }   // todo!() in the reference
+  void wait_result() { check(bz_poseidon_wait_result(h_)); }                                           // todo!() in the reference
+  std::optional<std::vector<PoseidonResult>> result(std::optional<size_t> expected_result) {
+    if (!expected_result) throw DriverClientError(DriverClientError::InvalidPrimitiveParam, "result(None)");
+    size_t cap = std::max<size_t>(*expected_result, get_num_of_pending_results()) + 8, got = 0;
+    std::vector<uint8_t> buf(cap * 64);
+    check(bz_poseidon_result(h_, *expected_result, buf.data(), cap, &got));
+    buf.resize(got * 64);
+    return PoseidonResult::parse_poseidon_hash_results(buf);
+  }
+  uint32_t get_last_element_sent_to_ring() { uint32_t v; check(bz_poseidon_get_last_element_sent_to_ring(h_, &v)); return v; }
+  uint32_t get_num_of_pending_results() { uint32_t v; check(bz_poseidon_get_num_of_pending_results(h_, &v)); return v; }
+  std::vector<uint8_t> get_raw_results(uint32_t n) { std::vector<uint8_t> v((size_t)n * 64); check(bz_poseidon_get_raw_results(h_, n, v.data())); return v; }
+  uint32_t get_last_hash_sent_to_host() { uint32_t v; check(bz_poseidon_get_last_hash_sent_to_host(h_, &v)); return v; }
+  DriverClient dclient;   // pub field `dclient` in the reference (poseidon_api.rs:15-17)
+
+ private:
+  bz_poseidon* h_ = nullptr;
 };
 
 }  // namespace ingo_blaze

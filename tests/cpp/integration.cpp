@@ -1,0 +1,251 @@
+// C++ counterparts of the reference's hardware integration tests, written against the C++ mirror of its Rust
+// surface (blaze_b200/host/blaze.hpp over the C ABI) so that they read like the originals:
+//   /root/reference/tests/integration_msm.rs      msm_bls12_381_test :150-207, msm_bls12_377_test :95-147,
+//                                                 msm_bn254_test :210-263, msm_bls12_381_precompute_test :285-372
+//   /root/reference/tests/integration_msm_hbm.rs  hbm_msm_bls12_381_test :121-226 (load once, scalars-only tasks)
+//   /root/reference/tests/integration_ntt.rs      ntt_test_correctness :6-60, pipelined :63-146
+//   /root/reference/tests/integration_poseidon.rs test_build_small_tree :123-169
+// Inputs follow tests/msm/mod.rs: 256 random (point, scalar) pairs tiled to MSM_SIZE (:21-31, :92-109), x8
+// precomputed records 2^(32 i) P (:360-380); but seeded, and the expected value comes from the CPU oracle
+// (oracle/liboracle.so -- the role arkworks plays in the reference's tests).  Where the reference asserts
+// "is_on_curve && to_string() equal" (:405-411) this asserts on-curve and BYTE equality of the normalised record.
+// Env: ID (device, default "0"), MSM_SIZE (default 8192) -- the reference's own knobs (integration_msm.rs:15-21).
+#include <cassert>
+#define CHECK(x) do { if (!(x)) { fprintf(stderr, "\nFAILED %s:%d: %s\n", __FILE__, __LINE__, #x); exit(1); } } while (0)   // active in release builds too
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <string>
+
+#include "../../blaze_b200/host/blaze.hpp"
+
+using namespace ingo_blaze;
+
+extern "C" {   // oracle/cpp/oracle.cpp (test infrastructure: the checker, never the thing measured)
+int orc_msm_naive(int curve, const uint8_t* bases, const uint8_t* scalars, uint64_t n, int factor, int threads, uint8_t* out);
+int orc_msm_pippenger(int curve, const uint8_t* bases, const uint8_t* scalars, uint64_t n, int threads, uint8_t* out);
+int orc_point_mul(int curve, const uint8_t* point, const uint8_t* scalar32, uint8_t* out);
+int orc_on_curve(int curve, const uint8_t* p);
+int orc_ntt(int curve, uint8_t* data, int log_n, int inverse, int threads);
+}
+
+static std::vector<uint8_t> from_hex_le(const char* hex, size_t nbytes) {
+  std::vector<uint8_t> v(nbytes, 0);
+  size_t len = strlen(hex);
+  for (size_t i = 0; i < len; i++) {
+    char ch = hex[len - 1 - i];
+    uint8_t d = ch <= '9' ? ch - '0' : (ch | 0x20) - 'a' + 10;
+    v[i / 2] |= d << (4 * (i & 1));
+  }
+  return v;
+}
+
+struct CurveInfo { Curve curve; int code; size_t fq; const char *gx, *gy, *r; };
+static const CurveInfo BLS381 = {Curve::BLS381, BZ_CURVE_BLS381, 48,
+  "17f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb",
+  "8b3f481e3aaa0f1a09e30ed741d8ae4fcf5e095d5d00af600db18cb2c04b3edd03cc744a2888ae40caa232946c5e7e1",
+  "73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001"};
+static const CurveInfo BLS377 = {Curve::BLS377, BZ_CURVE_BLS377, 48,
+  "8848defe740a67c8fc6225bf87ff5485951e2caa9d41bb188282c8bd37cb5cd5481512ffcd394eeab9b16eb21be9ef",
+  "1914a69c5102eff1f674f5d30afeec4bd7fb348ca3e52d96d182ad44fb82305c2fe3d3634a9591afd82de55559c8ea6",
+  "12ab655e9a2ca55660b44d1e5c37b00159aa76fed00000010a11800000000001"};
+static const CurveInfo BN254 = {Curve::BN254, BZ_CURVE_BN254, 32, "1", "2",
+  "30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001"};
+
+// a canonical scalar < r: random 32 bytes with the top byte cleared to below r's top byte
+static std::vector<uint8_t> random_scalar(std::mt19937_64& rng, const CurveInfo& c) {
+  std::vector<uint8_t> s(32), r = from_hex_le(c.r, 32);
+  for (auto& b : s) b = (uint8_t)rng();
+  s[31] = r[31] ? s[31] % r[31] : 0;
+  return s;
+}
+
+struct Inputs { std::vector<uint8_t> points, scalars, expected; };
+
+// tests/msm/mod.rs input_generator_*: 256 random pairs tiled to `n`; factor 8 appends 2^(32 i) P to every record
+static Inputs input_generator(const CurveInfo& c, size_t n, uint32_t factor, uint64_t seed) {
+  std::mt19937_64 rng(seed);
+  const size_t ps = 2 * c.fq, block = 256;
+  std::vector<uint8_t> g = from_hex_le(c.gx, c.fq), gy = from_hex_le(c.gy, c.fq);
+  g.insert(g.end(), gy.begin(), gy.end());
+  std::vector<uint8_t> pts(block * ps), scs(block * 32);
+  for (size_t k = 0; k < block; k++) {
+    std::vector<uint8_t> kk = random_scalar(rng, c), s = random_scalar(rng, c);
+    int inf = orc_point_mul(c.code, g.data(), kk.data(), pts.data() + k * ps);
+    CHECK(!inf);
+    memcpy(scs.data() + k * 32, s.data(), 32);
+  }
+  Inputs in;
+  std::vector<uint8_t> base_points(n * ps);
+  in.points.resize(n * ps * factor);
+  in.scalars.resize(n * 32);
+  for (size_t k = 0; k < n; k++) {
+    const uint8_t* p = pts.data() + (k % block) * ps;
+    memcpy(base_points.data() + k * ps, p, ps);
+    memcpy(in.scalars.data() + k * 32, scs.data() + (k % block) * 32, 32);
+    uint8_t* rec = in.points.data() + k * ps * factor;
+    memcpy(rec, p, ps);
+    for (uint32_t i = 1; i < factor; i++) {
+      if (k >= block) { memcpy(rec + i * ps, in.points.data() + (k % block) * ps * factor + i * ps, ps); continue; }
+      uint8_t coeff[32] = {0};
+      coeff[4 * i] = 1;   // 2^(32 i)
+      orc_point_mul(c.code, p, coeff, rec + i * ps);
+    }
+  }
+  in.expected.resize(3 * c.fq);
+  orc_msm_pippenger(c.code, base_points.data(), in.scalars.data(), n, 0, in.expected.data());
+  return in;
+}
+
+// tests/msm/mod.rs result_check_*: (is_on_curve, is_eq) from the Z||Y||X record
+static std::pair<bool, bool> result_check(const CurveInfo& c, const std::vector<uint8_t>& result, const Inputs& in) {
+  std::vector<uint8_t> xy(2 * c.fq);
+  memcpy(xy.data(), result.data() + 2 * c.fq, c.fq);   // X
+  memcpy(xy.data() + c.fq, result.data() + c.fq, c.fq);   // Y   (Z = 1: the record is normalised)
+  bool z_one = result[0] == 1;
+  for (size_t i = 1; i < c.fq; i++) z_one = z_one && result[i] == 0;
+  return {z_one && orc_on_curve(c.code, xy.data()) == 1, result == in.expected};
+}
+
+static std::string ID() { const char* e = getenv("ID"); return e ? e : "0"; }
+static uint32_t MSM_SIZE() { const char* e = getenv("MSM_SIZE"); return e ? (uint32_t)atoi(e) : 8192; }
+
+static void msm_dma_test(const CurveInfo& c, bool precompute) {
+  const uint32_t msm_size = MSM_SIZE();
+  Inputs in = input_generator(c, msm_size, precompute ? PRECOMPUTE_FACTOR : PRECOMPUTE_FACTOR_BASE, 11 + c.code);
+  DriverClient dclient(ID(), DriverConfig::driver_client_cfg(CardType::C1100));
+  MSMClient driver(MSMInit{PointMemoryType::DMA, precompute, c.curve}, std::move(dclient));
+  auto params = driver.loaded_binary_parameters();
+  CHECK(params.size() == 2);
+  driver.is_msm_engine_ready();
+  driver.task_label();
+  driver.driver_client.firewalls_status();
+  MSMParams msm_params{msm_size, std::nullopt};
+  driver.initialize(msm_params);
+  driver.start_process();
+  driver.set_data(MSMInput{in.points, in.scalars, msm_params});
+  driver.driver_client.firewalls_status();
+  driver.task_label();
+  driver.wait_result();
+  MSMResult mres = driver.result().value();
+  auto [is_on_curve, is_eq] = result_check(c, mres.result, in);
+  CHECK(is_on_curve);
+  CHECK(is_eq);
+}
+
+static void hbm_msm_bls12_381_test() {
+  const CurveInfo& c = BLS381;
+  const uint32_t msm_size = MSM_SIZE();
+  Inputs in = input_generator(c, msm_size, PRECOMPUTE_FACTOR_BASE, 21);
+  DriverClient dclient(ID(), DriverConfig::driver_client_cfg(CardType::C1100));
+  MSMClient driver(MSMInit{PointMemoryType::HBM, false, c.curve}, std::move(dclient));
+  const uint64_t hbm_addr = 0x0, offset = 0x0;
+  MSMParams msm_params{msm_size, std::make_pair(hbm_addr, offset)};
+  driver.load_data_to_hbm(in.points, hbm_addr, offset);
+  CHECK(driver.get_data_from_hbm(in.points.size(), hbm_addr, offset) == in.points);
+  uint32_t last_label = 0;
+  for (int it = 0; it < 3; it++) {   // the second task derives the table of window multiples; same bytes every time
+    driver.initialize(msm_params);
+    driver.start_process();
+    driver.set_data(MSMInput{std::nullopt, in.scalars, msm_params});
+    driver.wait_result();
+    MSMResult mres = driver.result().value();
+    auto [is_on_curve, is_eq] = result_check(c, mres.result, in);
+    CHECK(is_on_curve);
+    CHECK(is_eq);
+    CHECK(it == 0 || mres.result_label == last_label + 1);
+    last_label = mres.result_label;
+  }
+  CHECK(driver.plan_info().merged_table);
+}
+
+static void ntt_test_correctness_and_pipeline() {
+  // the reference core is fixed at 2^27 (ntt_data.rs:65-66) and is checked against golden files that are not in
+  // its repository; here: 2^16 through the same calls, against the oracle's arkworks-semantics radix-2 FFT
+  const int log_n = 16;
+  const size_t n = (size_t)1 << log_n;
+  std::mt19937_64 rng(5);
+  std::vector<std::vector<uint8_t>> ins(3, std::vector<uint8_t>(n * 32)), exps;
+  for (auto& d : ins) {
+    for (auto& b : d) b = (uint8_t)rng();
+    for (size_t i = 0; i < n; i++) d[i * 32 + 31] &= 0x3f;   // canonical: < 2^254 < r
+    exps.push_back(d);
+    orc_ntt(BZ_CURVE_BLS381, exps.back().data(), log_n, 0, 0);
+  }
+  DriverClient dclient(ID(), DriverConfig::driver_client_cfg(CardType::C1100));
+  NTTClient driver(std::move(dclient), Curve::BLS381, log_n, false);
+  const size_t buf_host = 0, buf_kernel = 0;
+  driver.set_data(NTTInput{buf_host, ins[0]});           // integration_ntt.rs:36-41
+  driver.driver_client.initialize_cms();
+  driver.driver_client.reset_sensor_data();
+  driver.initialize(NttInit{});
+  driver.start_process(buf_kernel);
+  driver.wait_result();
+  CHECK(driver.result(buf_kernel).value() == exps[0]);
+  // double-buffer cycle (integration_ntt.rs:103-136)
+  size_t h = 1;
+  driver.set_data(NTTInput{h, ins[1]});
+  driver.start_process(h);
+  driver.wait_result();
+  driver.set_data(NTTInput{1 - h, ins[2]});
+  driver.start_process(1 - h);                           // transform slot 1-h ...
+  CHECK(driver.result(h).value() == exps[1]);           // ... while slot h is read out
+  driver.wait_result();
+  CHECK(driver.result(1 - h).value() == exps[2]);
+}
+
+static void test_build_small_tree() {
+  const size_t TREE_HEIGHT_4_NUM_OF_NODES = 585;          // integration_poseidon.rs:23
+  DriverClient dclient(ID(), DriverConfig::driver_client_cfg(CardType::C1100));
+  PoseidonClient poseidon(Hash::Poseidon, std::move(dclient));
+  PoseidonInitializeParameters params{4, TreeMode::TreeC, ""};
+  uint32_t nof_elements = num_of_elements_in_base_layer(params.tree_height);
+  poseidon.initialize(params);
+  poseidon.loaded_binary_parameters();
+  // TEST_SCALAR (integration_poseidon.rs:24-25), BigUint::to_bytes_le
+  std::vector<uint8_t> scalar = from_hex_le("21e920e47484064714af44e765328a495be5412a30aa0834747b2225d86b66e8", 32);
+  for (uint32_t i = 0; i < nof_elements; i++)
+    for (int j = 0; j < 11; j++) poseidon.set_data(scalar);
+  auto result = poseidon.result(TREE_HEIGHT_4_NUM_OF_NODES).value();
+  CHECK(result.size() == TREE_HEIGHT_4_NUM_OF_NODES);
+  CHECK(num_of_elements_oct_tree(4) == TREE_HEIGHT_4_NUM_OF_NODES);
+}
+
+static void error_behaviour() {
+  DriverClient dclient(ID(), DriverConfig::driver_client_cfg(CardType::B200));
+  MSMClient driver(MSMInit{PointMemoryType::HBM, false, Curve::BLS381}, std::move(dclient));
+  bool threw = false;
+  try { driver.initialize(MSMParams{16, std::nullopt}); }   // HBM without an address: the reference panics (msm_api.rs:84)
+  catch (const DriverClientError& e) { threw = e.variant == DriverClientError::InvalidPrimitiveParam; }
+  CHECK(threw);
+  threw = false;
+  try { driver.wait_result(); } catch (const DriverClientError& e) { threw = e.variant == DriverClientError::NoResult; }
+  CHECK(threw);
+}
+
+int main(int argc, char** argv) {
+  std::string only = argc > 1 ? argv[1] : "";
+  struct T { const char* name; void (*fn)(); };
+  const T tests[] = {
+      {"msm_bls12_381_test", [] { msm_dma_test(BLS381, false); }},
+      {"msm_bls12_377_test", [] { msm_dma_test(BLS377, false); }},
+      {"msm_bn254_test", [] { msm_dma_test(BN254, false); }},
+      {"msm_bls12_381_precompute_test", [] { msm_dma_test(BLS381, true); }},
+      {"hbm_msm_bls12_381_test", hbm_msm_bls12_381_test},
+      {"ntt_test_correctness_and_pipeline", ntt_test_correctness_and_pipeline},
+      {"test_build_small_tree", test_build_small_tree},
+      {"error_behaviour", error_behaviour},
+  };
+  int ran = 0;
+  for (const T& t : tests) {
+    if (!only.empty() && only != t.name) continue;
+    printf("test %s ... ", t.name);
+    fflush(stdout);
+    t.fn();
+    printf("ok\n");
+    ran++;
+  }
+  printf("%d passed\n", ran);
+  return ran ? 0 : 1;
+}
