@@ -361,6 +361,8 @@ def main():
     # resident points: P_i = P0 + i*Q for this rank's index range, generated on the device (untimed)
     m.generate_chain_points(p0 + q, first, per, HBM_ADDR, 0)
     params = bz.MSMParams(per, (HBM_ADDR, 0))
+    if world > 1:
+        m.set_raw_result(True)   # shards stay projective; the combine normalises once
 
     # scalars: pinned host copy (for e2e) + device copy (for value)
     sc_np = random_scalars(c, N, seed=4242)[first * 32:(first + per) * 32]

@@ -55,6 +55,7 @@ SIGNATURES = {
     "bz_msm_plan_info": [vp, u32p],
     "bz_msm_plan_info_ex": [vp, u32p],
     "bz_msm_set_precompute": [vp, i32],
+    "bz_msm_set_raw_result": [vp, i32],
     "bz_msm_set_scalars_device": [vp, u64, u32, i32, u64, u64],
     "bz_msm_combine_results": [vp, vp, i32, vp, sz],
     "bz_msm_generate_chain_points": [vp, vp, sz, u64, u64, u64, u64],

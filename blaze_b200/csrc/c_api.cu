@@ -294,6 +294,7 @@ struct bz_msm {
   uint64_t wtable_n = 0, wtable_addr = ~0ull, wtable_epoch = 0;
   int wtable_c = 0, wtable_levels = 0;
   int precomp_mode = 1;
+  int raw_result = 0;            // bz_msm_set_raw_result
   bool precomp_failed = false;   // allocation failed for this point set: stay on the plain table
   uint64_t table_uses = 0;       // MSMs launched on the current arena table
   uint8_t* comb_dev = nullptr;   // scratch of bz_msm_combine_results
@@ -718,6 +719,7 @@ static int32_t launch_task(bz_msm* m) {
     m->table_pending = false;
   }
   cudaEventRecord(m->ev[1], st);
+  m->plan.raw_result = m->raw_result;
   m->ops->bucket_phase(m->plan, m->ws, merged ? m->wtable : m->table, st);
   cudaEventRecord(m->ev[4], st);
   m->timed = true;
@@ -977,6 +979,12 @@ extern "C" int32_t bz_msm_set_precompute(bz_msm* m, int32_t mode) {
   std::lock_guard<std::mutex> lk(m->mu);
   m->precomp_mode = mode;
   m->precomp_failed = false;
+  return BZ_OK;
+}
+extern "C" int32_t bz_msm_set_raw_result(bz_msm* m, int32_t raw) {
+  if (!m) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null MSMClient");
+  std::lock_guard<std::mutex> lk(m->mu);
+  m->raw_result = raw ? 1 : 0;
   return BZ_OK;
 }
 extern "C" int32_t bz_msm_plan_info_ex(bz_msm* m, uint32_t out[8]) {

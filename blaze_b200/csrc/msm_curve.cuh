@@ -100,6 +100,17 @@ struct dev {
 #pragma unroll
     for (int k = 0; k < N; k++) w[k] = r.v[k];
   }
+  // Z||Y||X homogeneous projective WITHOUT the normalising inversion (x = X/Z, y = Y/Z -- the reference's own
+  // result format, tests/msm/mod.rs:397-403): X' = X ZZZ, Y' = Y ZZ, Z' = ZZ ZZZ.  For shards of a multi-GPU
+  // MSM, whose records are summed (and normalised once) by k_combine_results.
+  __device__ static void store_result_raw(uint8_t* out, const XYZZ<C>& p) {
+    uint32_t* w = reinterpret_cast<uint32_t*>(out);
+    for (int k = 0; k < 3 * N; k++) w[k] = 0;
+    if (G::is_inf(p)) { w[N] = 1; return; }
+    store_canonical(out, F::mul(p.ZZ, p.ZZZ));
+    store_canonical(out + 4 * N, F::mul(p.Y, p.ZZ));
+    store_canonical(out + 8 * N, F::mul(p.X, p.ZZZ));
+  }
   // Z||Y||X with Z = 1 (infinity: Z=0, Y=1, X=0), canonical LE
   __device__ static void store_result(uint8_t* out, const XYZZ<C>& p) {
     Affine<C> a;
@@ -522,7 +533,7 @@ k_reduce_level(const XyzzM<C>* __restrict__ A, const XyzzM<C>* __restrict__ Vin,
 
 // Horner over the window sums, normalise, serialise
 template <class C>
-__global__ void k_finish(const XyzzM<C>* __restrict__ win, int W, int c, uint8_t* __restrict__ result) {
+__global__ void k_finish(const XyzzM<C>* __restrict__ win, int W, int c, int raw, uint8_t* __restrict__ result) {
   typedef dev<C> D;
   typedef ec<C> G;
   if (blockIdx.x || threadIdx.x) return;
@@ -532,7 +543,8 @@ __global__ void k_finish(const XyzzM<C>* __restrict__ win, int W, int c, uint8_t
     XYZZ<C> v = D::load_xyzz(win + w);
     G::add(acc, v);
   }
-  D::store_result(result, acc);
+  if (raw) D::store_result_raw(result, acc);
+  else D::store_result(result, acc);
 }
 
 // sum n canonical result records
@@ -700,7 +712,7 @@ struct CurveLaunch {
       perm_bits = -1;
       level++;
     }
-    k_finish<C><<<1, 32, 0, st>>>(top, p.W, p.c, ws.result);
+    k_finish<C><<<1, 32, 0, st>>>(top, p.W, p.c, p.raw_result, ws.result);
   }
   static void build_wtable(void* wtable, uint64_t n, int levels, int c, cudaStream_t st) {
     constexpr int K = 16;

@@ -60,6 +60,7 @@ struct MsmPlan {
   uint32_t nb;             // bucket slots per window = 2^kb
   uint32_t seg_len;        // sorted entries per accumulate thread
   uint64_t nseg;           // number of accumulate segments = ceil(W*M / seg_len)
+  int raw_result;          // 1: result record left projective (Z != 1): shard of a multi-GPU MSM, normalised by the combine
   int tma_stage;           // 1: k_accumulate_tma (points staged through shared memory by cp.async.bulk), 0: register prefetch
   int batch_affine;        // 1: accumulate buckets by batched affine addition (msm_ba.cuh), 0: XYZZ sweep
   uint32_t chunk;          // entries per reduce thread at every level of the running-sum recursion (power of two)

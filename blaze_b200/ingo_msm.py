@@ -166,6 +166,10 @@ class MSMClient(DriverPrimitive):
         (default), 2 immediately.  Same results in every mode."""
         check(lib().bz_msm_set_precompute(self._h, int(mode)))
 
+    def set_raw_result(self, raw=True):
+        """Leave result records projective (Z != 1, the reference's own format): for shards summed by combine_results."""
+        check(lib().bz_msm_set_raw_result(self._h, 1 if raw else 0))
+
     def set_scalars_device(self, dev_ptr, params: MSMParams):
         has, a, o = _hbm(params)
         check(lib().bz_msm_set_scalars_device(self._h, int(dev_ptr), params.nof_elements, has, a, o))

@@ -129,6 +129,10 @@ int32_t bz_msm_plan_info_ex(bz_msm* m, uint32_t out[8]);
  * MSM over an unchanged point set; 2: immediately.  Results are identical in every mode.  Env BZ_MSM_PRECOMP
  * sets the default. */
 int32_t bz_msm_set_precompute(bz_msm* m, int32_t mode);
+/* raw = 1: result records stay homogeneous projective with Z != 1 (x = X/Z, y = Y/Z -- the reference's own result
+ * format, tests/msm/mod.rs:397-403) instead of being normalised to Z = 1: saves the field inversion per task for
+ * the shards of a multi-GPU MSM, whose records bz_msm_combine_results sums and normalises once.  Default 0. */
+int32_t bz_msm_set_raw_result(bz_msm* m, int32_t raw);
 /* like set_data(points=None) but the scalars already live in device memory (device pointer) */
 int32_t bz_msm_set_scalars_device(bz_msm* m, uint64_t scalars_dev_ptr, uint32_t nof_elements, int32_t has_hbm_addr,
                                   uint64_t hbm_addr, uint64_t hbm_offset);

@@ -499,3 +499,30 @@ def test_msm_merged_table_tiny_inputs(dclient, oracle, n):
         assert m.plan_info()["merged_table"]
     finally:
         m.close()
+
+
+def test_msm_raw_projective_result_and_combine(dclient, oracle):
+    """Shards of a point-sharded multi-GPU MSM keep their record projective (Z != 1: the reference's own result
+    format, tests/msm/mod.rs:397-403); combine_results sums the shard records and normalises once."""
+    c = CURVE_BY_NAME["BLS12_381"]
+    n = 4000
+    pts, p0, q = chain_points(c, n, seed=500)
+    sc = random_scalars(c, n, seed=501)
+    exp = oracle.chain_expected("BLS12_381", p0, q, sc, n)
+    m = MSMClient.new(MSMInit(PointMemoryType.HBM, False, Curve.BLS381), dclient)
+    try:
+        m.set_raw_result(True)
+        half = n // 2
+        recs = []
+        for lo, cnt, addr in ((0, half, 0), (half, n - half, 0x1000000)):
+            m.load_data_to_hbm(pts[lo * 96:(lo + cnt) * 96], addr, 0)
+            params = MSMParams(cnt, (addr, 0))
+            rec = run_hbm(m, params, sc[lo * 32:(lo + cnt) * 32])
+            assert rec[:48] != (1).to_bytes(48, "little")          # not normalised
+            recs.append(rec)
+        assert oracle.normalize_result("BLS12_381", recs[0]) == oracle.chain_expected("BLS12_381", p0, q, sc[:half * 32], half)
+        assert m.combine_results(b"".join(recs), 2) == exp
+        m.set_raw_result(False)
+        assert run_hbm(m, MSMParams(half, (0, 0)), sc[:half * 32]) == oracle.normalize_result("BLS12_381", recs[0])
+    finally:
+        m.close()
