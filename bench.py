@@ -401,8 +401,11 @@ def main():
 
     # ---- warm-up (also builds the Montgomery table and the workspace)
     res = None
+    warm_s = []
     for _ in range(max(args.warmup, 3)):
+        t0 = time.perf_counter()
         res = combine(step_resident())
+        warm_s.append(round(time.perf_counter() - t0, 3))   # step 2 contains the one-off build of the merged table
 
     # ---- verification at full size: closed form of the chain workload (bit-exact)
     verified = None
@@ -527,6 +530,7 @@ def main():
                 "phase_ms": {"sort": sum(sort_ms) / len(sort_ms), "accumulate": sum(acc_ms) / len(acc_ms),
                              "reduce": sum(red_ms) / len(red_ms)},
                 "device_ms_per_step": dev_step_ms,
+                "warmup_step_s": warm_s,
             },
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": per * 32 * world,
                     "d2h_bytes_per_step": c.result_point_size * world, "ms_per_step": 1e3 * wall_e2e / args.steps,
