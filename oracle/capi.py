@@ -35,6 +35,7 @@ def lib():
         _LIB.orc_chain_points.argtypes = [i, u8p, u8p, u64, ctypes.c_void_p]
         _LIB.orc_chain_expected.argtypes = [i, u8p, u8p, ctypes.c_void_p, u64, u64, u8p]
         _LIB.orc_ntt.argtypes = [i, ctypes.c_void_p, i, i, i]
+        _LIB.orc_ntt_eval.argtypes = [i, ctypes.c_void_p, i, i, ctypes.c_void_p, i, ctypes.c_void_p, i]
         _LIB.orc_fq_mul.argtypes = [i, u8p, u8p, u8p]
         _LIB.orc_fr_mul.argtypes = [i, u8p, u8p, u8p]
     return _LIB
@@ -115,6 +116,18 @@ def ntt(curve, data, log_n: int, inverse=False, threads=0):
     rc = lib().orc_ntt(_code(curve), data.ctypes.data, log_n, 1 if inverse else 0, threads or hw_threads())
     assert rc == 0, rc
     return data
+
+
+def ntt_eval(curve, data, log_n: int, ks, inverse=False, threads=0):
+    """Outputs k in `ks` of the size-2^log_n transform of `data` (numpy uint8, canonical 32-byte LE elements), straight
+    from the definition out[k] = sum_j in[j] w^(jk) (Horner, O(n) per point).  Returns a list of ints."""
+    import numpy as np
+    kk = np.asarray(list(ks), dtype=np.uint64)
+    out = np.zeros(32 * len(kk), dtype=np.uint8)
+    rc = lib().orc_ntt_eval(_code(curve), data.ctypes.data, log_n, 1 if inverse else 0, kk.ctypes.data, len(kk),
+                            out.ctypes.data, threads or hw_threads())
+    assert rc == 0, rc
+    return [int.from_bytes(bytes(out[32 * i:32 * i + 32]), "little") for i in range(len(kk))]
 
 
 def fq_mul(curve, a: bytes, b: bytes) -> bytes:

@@ -525,6 +525,56 @@ static int ntt_impl(const Field<4>& fr, int gen, int two_adicity, uint8_t* data,
   return 0;
 }
 
+
+// out[i] = sum_j in[j] x_i^j with x_i = w^(k_i): the DEFINITION of output k_i of the size-2^log_n transform,
+// evaluated by Horner in O(n) per point -- lets tests and bench.py spot-check a 2^27 transform without a 60 s
+// CPU FFT.  `data` holds canonical 32-byte LE elements (reduced here if >= r) and is not modified.
+static int ntt_eval_impl(const Field<4>& fr, int gen, int two_adicity, const uint8_t* data, int log_n, int inverse,
+                         const uint64_t* ks, int nk, uint8_t* out, int threads) {
+  if (log_n > two_adicity) return -2;
+  const u64 n = 1ull << log_n;
+  u64 w_n[4];
+  fr_root(fr, gen, two_adicity, log_n, inverse != 0, w_n);
+  const int nchunk = (int)std::min<u64>(std::max<u64>(1, n / 65536), 64);
+  const u64 per = n / nchunk;
+  std::vector<u64> part((size_t)4 * nk * nchunk);
+  std::vector<u64> xs((size_t)4 * nk);
+  for (int i = 0; i < nk; i++) {
+    u64 e[4] = {ks[i] & (n - 1), 0, 0, 0};
+    fr.pow(&xs[4 * i], w_n, e, 1);
+  }
+  parallel_for(nk * nchunk, threads, [&](int job) {
+    const int i = job / nchunk, c = job % nchunk;
+    const u64* x = &xs[4 * i];   // Montgomery form: mont_mul(canonical, x R) = canonical * x
+    u64 acc[4] = {0, 0, 0, 0};
+    for (u64 j = (u64)(c + 1) * per; j-- > (u64)c * per;) {
+      u64 v[4];
+      memcpy(v, data + 32 * j, 32);
+      while (Field<4>::geq(v, fr.p)) Field<4>::sub_n(v, v, fr.p);
+      fr.mul(acc, acc, x);
+      fr.add(acc, acc, v);
+    }
+    memcpy(&part[4 * ((size_t)i * nchunk + c)], acc, 32);
+  });
+  for (int i = 0; i < nk; i++) {
+    // total = sum_c part_c * x^(c per), Horner over the chunks with step x^per
+    u64 e[4] = {per, 0, 0, 0}, xp[4], acc[4] = {0, 0, 0, 0};
+    fr.pow(xp, &xs[4 * i], e, 1);
+    for (int c = nchunk; c-- > 0;) {
+      fr.mul(acc, acc, xp);
+      fr.add(acc, acc, &part[4 * ((size_t)i * nchunk + c)]);
+    }
+    if (inverse) {
+      u64 nn[4] = {n, 0, 0, 0}, ninv[4];
+      fr.to_mont(ninv, nn);
+      fr.inverse(ninv, ninv);
+      fr.mul(acc, acc, ninv);
+    }
+    memcpy(out + 32 * i, acc, 32);
+  }
+  return 0;
+}
+
 // ------------------------------------------------------------------ entry-point bodies
 template <int NL>
 static int point_mul(const Curve<NL>& C, const uint8_t* point, const uint8_t* scalar32, uint8_t* out) {
@@ -701,6 +751,15 @@ int orc_ntt(int curve, uint8_t* data, int log_n, int inverse, int threads) {
   if (curve == 2) return ntt_impl(C381.fr, 7, 32, data, log_n, inverse, threads);
   if (curve == 0) return ntt_impl(C377.fr, 22, 47, data, log_n, inverse, threads);
   if (curve == 1) return ntt_impl(C254.fr, 5, 28, data, log_n, inverse, threads);
+  return -1;
+}
+// out[i] = output k_i of the size-2^log_n transform of `data`, from the definition (O(n) per point)
+int orc_ntt_eval(int curve, const uint8_t* data, int log_n, int inverse, const uint64_t* ks, int nk, uint8_t* out,
+                 int threads) {
+  init_all();
+  if (curve == 2) return ntt_eval_impl(C381.fr, 7, 32, data, log_n, inverse, ks, nk, out, threads);
+  if (curve == 0) return ntt_eval_impl(C377.fr, 22, 47, data, log_n, inverse, ks, nk, out, threads);
+  if (curve == 1) return ntt_eval_impl(C254.fr, 5, 28, data, log_n, inverse, ks, nk, out, threads);
   return -1;
 }
 int orc_fq_mul(int curve, const uint8_t* a, const uint8_t* b, uint8_t* out) {

@@ -25,7 +25,7 @@ from .curves import BLS12_381
 
 R_ = BLS12_381.r
 R_F = 8
-R_P = {9: 57, 12: 57}
+R_P = {3: 57, 9: 57, 12: 57}
 TREE_C, TREE_D = 0, 1       # ingo_hash/utils.rs:16-30 (TreeMode::value)
 
 
@@ -65,21 +65,39 @@ class Grain:
 
 
 _CACHE = {}
+MDS_CAUCHY, MDS_GRAIN = 0, 1
 
 
-def params(t):
-    """(round_constants[(R_F+R_P)*t], mds[t][t]) for width t."""
-    if t not in _CACHE:
+def params(t, mds_mode=MDS_CAUCHY):
+    """(round_constants[(R_F+R_P)*t], mds[t][t]) for width t.
+    MDS_CAUCHY: M[i][j] = 1/(i + t + j) (Filecoin neptune; what PoseidonClient uses).
+    MDS_GRAIN : x_i, y_j drawn from the same Grain stream right after the round constants (the Poseidon reference
+                generator, generate_parameters_grain.sage: create_mds_p) -- the parameter set of the published
+                test vectors (tests/golden/external_kats.json)."""
+    key = (t, mds_mode)
+    if key not in _CACHE:
         g = Grain(255, t, R_F, R_P[t])
         rc = [g.field_element(255, R_) for _ in range((R_F + R_P[t]) * t)]
-        mds = [[pow(i + (t + j), -1, R_) for j in range(t)] for i in range(t)]
-        _CACHE[t] = (rc, mds)
-    return _CACHE[t]
+        if mds_mode == MDS_CAUCHY:
+            mds = [[pow(i + (t + j), -1, R_) for j in range(t)] for i in range(t)]
+        else:
+            def bits(n):
+                v = 0
+                for _ in range(n):
+                    v = (v << 1) | g.bit()
+                return v
+            while True:
+                xy = [bits(255) % R_ for _ in range(2 * t)]
+                if len(set(xy)) == 2 * t and all((x + y) % R_ for x in xy[:t] for y in xy[t:]):
+                    break
+            mds = [[pow(xy[i] + xy[t + j], -1, R_) for j in range(t)] for i in range(t)]
+        _CACHE[key] = (rc, mds)
+    return _CACHE[key]
 
 
-def permute(state):
+def permute(state, mds_mode=MDS_CAUCHY):
     t = len(state)
-    rc, mds = params(t)
+    rc, mds = params(t, mds_mode)
     nr = R_F + R_P[t]
     s = list(state)
     for r in range(nr):

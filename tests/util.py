@@ -17,13 +17,32 @@ def seed_points(c, seed):
 
 
 def random_scalars(c, n, seed):
-    """n canonical scalars (< r) as a uint8 array of n*32 bytes."""
+    """n canonical scalars, uniform in [0, r), as a uint8 array of n*32 bytes (rejection sampling on
+    r.bit_length()-bit draws, vectorised)."""
     rng = np.random.default_rng(seed)
-    raw = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
-    top_bits = c.r.bit_length() - 1            # force < 2^(bits-1) <= r
-    keep = top_bits - 8 * 31
-    raw[:, 31] &= (1 << keep) - 1 if keep > 0 else 0
-    return raw.reshape(-1)
+    bits = c.r.bit_length()
+    top_mask = np.uint64((1 << (bits - 192)) - 1)
+    rw = [np.uint64((c.r >> (64 * k)) & 0xFFFFFFFFFFFFFFFF) for k in range(4)]
+
+    def draw(m):
+        w = rng.integers(0, 1 << 64, size=(m, 4), dtype=np.uint64)
+        w[:, 3] &= top_mask
+        return w
+
+    def ge_r(w):   # lexicographic (most significant word first) w >= r
+        ge = np.ones(len(w), dtype=bool)        # equal so far
+        res = np.zeros(len(w), dtype=bool)
+        for k in (3, 2, 1, 0):
+            res |= ge & (w[:, k] > rw[k])
+            ge &= w[:, k] == rw[k]
+        return res | ge
+
+    w = draw(n)
+    bad = np.nonzero(ge_r(w))[0]
+    while len(bad):
+        w[bad] = draw(len(bad))
+        bad = bad[ge_r(w[bad])]
+    return w.view(np.uint8).reshape(-1)
 
 
 def chain_points(c, n, seed=0):
