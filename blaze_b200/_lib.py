@@ -24,6 +24,10 @@ SIGNATURES = {
     "bz_kernel_launch_count": [],
     "bz_dclient_new": [ctypes.c_char_p, i32, ctypes.POINTER(vp)],
     "bz_dclient_free": [vp],
+    "bz_dclient_device_count": [vp, u32p],
+    "bz_comm_unique_id": [vp],
+    "bz_dclient_comm_init": [vp, i32, i32, vp],
+    "bz_dclient_comm_info": [vp, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)],
     "bz_dclient_reset": [vp],
     "bz_dclient_dma_write": [vp, u64, u64, vp, sz],
     "bz_dclient_dma_read": [vp, u64, u64, vp, sz],
@@ -52,6 +56,8 @@ SIGNATURES = {
     "bz_msm_sizes": [vp, u32p, u32p, u32p, u32p],
     "bz_msm_phase_times": [vp, ctypes.POINTER(ctypes.c_float)],
     "bz_msm_set_window_bits": [vp, i32],
+    "bz_msm_get_api": [vp, u32p, sz],
+    "bz_msm_table_build_ms": [vp, ctypes.POINTER(ctypes.c_float)],
     "bz_msm_plan_info": [vp, u32p],
     "bz_msm_plan_info_ex": [vp, u32p],
     "bz_msm_set_precompute": [vp, i32],
@@ -60,6 +66,7 @@ SIGNATURES = {
     "bz_msm_combine_results": [vp, vp, i32, vp, sz],
     "bz_msm_generate_chain_points": [vp, vp, sz, u64, u64, u64, u64],
     "bz_msm_field_selftest": [vp, vp, vp, vp, i32, i32],
+    "bz_msm_expand_precompute": [vp, u64, u64, u64],
     "bz_ntt_new": [vp, i32, ctypes.POINTER(vp)],
     "bz_ntt_new_ex": [vp, i32, i32, i32, ctypes.POINTER(vp)],
     "bz_ntt_free": [vp],
@@ -78,6 +85,7 @@ SIGNATURES = {
     "bz_ntt_dist_set_input": [vp, vp, sz],
     "bz_ntt_dist_get_output": [vp, vp, sz],
     "bz_ntt_dist_buffers": [vp, u64p, u64p, u64p],
+    "bz_ntt_dist_run": [vp],
     "bz_ntt_dist_step1": [vp],
     "bz_ntt_dist_sync": [vp],
     "bz_ntt_dist_step3": [vp],
@@ -95,6 +103,9 @@ SIGNATURES = {
     "bz_poseidon_get_num_of_pending_results": [vp, u32p],
     "bz_poseidon_get_raw_results": [vp, u32, vp],
     "bz_poseidon_get_last_hash_sent_to_host": [vp, u32p],
+    "bz_poseidon_device_ms": [vp, ctypes.POINTER(ctypes.c_float)],
+    "bz_poseidon_permute": [vp, i32, i32, vp, sz, vp],
+    "bz_poseidon_optimized_constants": [i32, i32, vp, sz, ctypes.POINTER(sz)],
 }
 _RESTYPES = {"bz_last_error": ctypes.c_char_p, "bz_version": ctypes.c_char_p, "bz_kernel_launch_count": ctypes.c_uint64}
 

@@ -1,16 +1,15 @@
-// Host side of libblaze_b200.so: the C ABI declared in include/blaze_b200.h, the DriverClient
-// device arena, and the MSMClient task state machine that drives the CUDA pipeline.
+// MSMClient, one device ("leaf"): the task state machine that drives the CUDA pipeline of msm_sort.cu / msm_curve.cuh.
+// The C ABI names of include/blaze_b200.h are defined in msm_api.cu and land here (directly, or once per member device
+// for a multi-device client).
 //
-// Mirrors (behaviour, not code) /root/reference/src/driver_client/dclient.rs and
-// /root/reference/src/ingo_msm/msm_api.rs: same call order tolerance
+// Mirrors (behaviour, not code) /root/reference/src/ingo_msm/msm_api.rs: same call order tolerance
 // (initialize -> start_process -> set_data -> wait_result -> result), same mode selection
 // ((mem_type, hbm_point_addr) -> DMA / HBM, msm_api.rs:75-95,163-216), same wire sizes
-// (msm_cfg.rs:44-92).  XDMA pwrite/pread become cudaMemcpyAsync into a device arena, register
-// polling becomes CUDA events.  No CPU fallback: without a device every constructor fails.
+// (msm_cfg.rs:44-92).  Register polling becomes CUDA events.  No CPU fallback.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <algorithm>
-#include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -21,181 +20,13 @@
 
 #include "../../include/blaze_b200.h"
 #include "api_common.h"
+#include "client_internal.h"
+#include "msm_client.h"
 #include "msm_internal.h"
 
 using namespace bz;
 
-// ------------------------------------------------------------------------------------ errors
-static thread_local std::string g_last_error;
-
-int32_t bz_fail(int32_t code, const char* fmt, ...) {
-  char buf[512];
-  va_list ap;
-  va_start(ap, fmt);
-  vsnprintf(buf, sizeof(buf), fmt, ap);
-  va_end(ap);
-  g_last_error = buf;
-  return code;
-}
-
 #define fail bz_fail
-
-std::atomic<uint64_t> bz::g_kernel_launches{0};
-extern "C" uint64_t bz_kernel_launch_count(void) { return bz::g_kernel_launches.load(); }
-extern "C" const char* bz_last_error(void) { return g_last_error.c_str(); }
-extern "C" const char* bz_version(void) { return "blaze_b200 0.1.0 sm_100a"; }
-
-// ------------------------------------------------------------------------------------ DriverClient
-// Card address space: [0, ARENA_LIMIT) is HBM (a growable device arena).  The MSM stream ports of
-// the reference (msm_cfg.rs:44-92: 0x0000_0100_0000_0000 / 0x0000_0200_0000_0000) lie above it and
-// are served by bz_msm_set_data, never by dma_write.
-static const uint64_t ARENA_LIMIT = 1ull << 40;
-static const size_t ARENA_GRAIN = 64ull << 20;
-
-struct bz_dclient {
-  int device = 0;
-  int card_type = BZ_CARD_B200;
-  cudaStream_t stream = nullptr;
-  uint8_t* arena = nullptr;
-  size_t arena_cap = 0;
-  uint64_t epoch = 1;   // bumped on every arena write: invalidates cached Montgomery tables
-  std::mutex mu;
-};
-
-cudaStream_t dc_stream(bz_dclient* dc);
-int dc_device(bz_dclient* dc);
-int32_t dc_select(bz_dclient* dc) {
-  if (!dc) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null DriverClient");
-  CUDA_TRY(BZ_ERR_NO_DEVICE, cudaSetDevice(dc->device));
-  return BZ_OK;
-}
-
-cudaStream_t dc_stream(bz_dclient* dc) { return dc->stream; }
-int dc_device(bz_dclient* dc) { return dc->device; }
-
-static int32_t arena_reserve(bz_dclient* dc, uint64_t end) {
-  if (end > ARENA_LIMIT) return fail(BZ_ERR_WRITE, "address 0x%llx beyond the HBM window", (unsigned long long)end);
-  if (end <= dc->arena_cap) return BZ_OK;
-  size_t cap = (size_t)((end + ARENA_GRAIN - 1) / ARENA_GRAIN * ARENA_GRAIN);
-  uint8_t* p = nullptr;
-  CUDA_TRY(BZ_ERR_WRITE, cudaMalloc(&p, cap));
-  if (dc->arena_cap) CUDA_TRY(BZ_ERR_WRITE, cudaMemcpyAsync(p, dc->arena, dc->arena_cap, cudaMemcpyDeviceToDevice, dc->stream));
-  CUDA_TRY(BZ_ERR_WRITE, cudaMemsetAsync(p + dc->arena_cap, 0, cap - dc->arena_cap, dc->stream));
-  CUDA_TRY(BZ_ERR_WRITE, cudaStreamSynchronize(dc->stream));
-  if (dc->arena) cudaFree(dc->arena);
-  dc->arena = p;
-  dc->arena_cap = cap;
-  return BZ_OK;
-}
-
-extern "C" int32_t bz_dclient_new(const char* id, int32_t card_type, bz_dclient** out) {
-  if (!out) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "out is null");
-  *out = nullptr;
-  int ndev = 0;
-  cudaError_t e = cudaGetDeviceCount(&ndev);
-  if (e != cudaSuccess || ndev == 0)
-    return fail(BZ_ERR_NO_DEVICE, "no CUDA device (%s); blaze_b200 has no CPU fallback",
-                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
-  int dev = id && *id ? atoi(id) : 0;
-  if (dev < 0 || dev >= ndev) return fail(BZ_ERR_NO_DEVICE, "device id '%s' out of range (%d devices)", id, ndev);
-  bz_dclient* dc = new bz_dclient();
-  dc->device = dev;
-  dc->card_type = card_type;
-  if (cudaSetDevice(dev) != cudaSuccess || cudaStreamCreateWithFlags(&dc->stream, cudaStreamNonBlocking) != cudaSuccess) {
-    delete dc;
-    return fail(BZ_ERR_NO_DEVICE, "cannot initialise device %d: %s", dev, cudaGetErrorString(cudaGetLastError()));
-  }
-  *out = dc;
-  return BZ_OK;
-}
-
-extern "C" int32_t bz_dclient_free(bz_dclient* dc) {
-  if (!dc) return BZ_OK;
-  cudaSetDevice(dc->device);
-  if (dc->stream) { cudaStreamSynchronize(dc->stream); cudaStreamDestroy(dc->stream); }
-  if (dc->arena) cudaFree(dc->arena);
-  delete dc;
-  return BZ_OK;
-}
-
-extern "C" int32_t bz_dclient_reset(bz_dclient* dc) {
-  int32_t rc = dc_select(dc);
-  if (rc) return rc;
-  std::lock_guard<std::mutex> lk(dc->mu);
-  // The reference toggles the DFX decoupler (dclient.rs:88-93): user logic is reset, HBM contents
-  // survive.  Here: drain the work stream; the arena keeps its bytes.
-  CUDA_TRY(BZ_ERR_UNKNOWN, cudaStreamSynchronize(dc->stream));
-  return BZ_OK;
-}
-
-extern "C" int32_t bz_dclient_dma_write(bz_dclient* dc, uint64_t base, uint64_t offset, const uint8_t* data, size_t len) {
-  int32_t rc = dc_select(dc);
-  if (rc) return rc;
-  if (!data && len) return fail(BZ_ERR_WRITE, "null data");
-  std::lock_guard<std::mutex> lk(dc->mu);
-  uint64_t a = base + offset;
-  if (a < base || a + len < a) return fail(BZ_ERR_WRITE, "address overflow");
-  rc = arena_reserve(dc, a + len);
-  if (rc) return rc;
-  CUDA_TRY(BZ_ERR_WRITE, cudaMemcpyAsync(dc->arena + a, data, len, cudaMemcpyHostToDevice, dc->stream));
-  CUDA_TRY(BZ_ERR_WRITE, cudaStreamSynchronize(dc->stream));   // caller may free `data` on return
-  dc->epoch++;
-  return BZ_OK;
-}
-
-extern "C" int32_t bz_dclient_dma_read(bz_dclient* dc, uint64_t base, uint64_t offset, uint8_t* out, size_t len) {
-  int32_t rc = dc_select(dc);
-  if (rc) return rc;
-  if (!out && len) return fail(BZ_ERR_READ, "null out");
-  std::lock_guard<std::mutex> lk(dc->mu);
-  uint64_t a = base + offset;
-  if (a + len > ARENA_LIMIT) return fail(BZ_ERR_READ, "address 0x%llx beyond the HBM window", (unsigned long long)a);
-  // never-written HBM reads back as zeros
-  size_t have = a < dc->arena_cap ? (size_t)std::min<uint64_t>(len, dc->arena_cap - a) : 0;
-  if (have) {
-    CUDA_TRY(BZ_ERR_READ, cudaMemcpyAsync(out, dc->arena + a, have, cudaMemcpyDeviceToHost, dc->stream));
-    CUDA_TRY(BZ_ERR_READ, cudaStreamSynchronize(dc->stream));
-  }
-  if (have < len) memset(out + have, 0, len - have);
-  return BZ_OK;
-}
-
-extern "C" int32_t bz_dclient_firewalls_status(bz_dclient* dc, uint32_t* blocked_mask) {
-  if (!dc) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null DriverClient");
-  if (blocked_mask) *blocked_mask = 0;
-  return BZ_OK;
-}
-extern "C" int32_t bz_dclient_unblock_firewalls(bz_dclient* dc) { return dc ? BZ_OK : fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null DriverClient"); }
-extern "C" int32_t bz_dclient_initialize_cms(bz_dclient* dc) { return dc ? BZ_OK : fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null DriverClient"); }
-extern "C" int32_t bz_dclient_reset_sensor_data(bz_dclient* dc) { return dc ? BZ_OK : fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null DriverClient"); }
-extern "C" int32_t bz_dclient_setup_before_load_binary(bz_dclient* dc) { return dc ? BZ_OK : fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null DriverClient"); }
-extern "C" int32_t bz_dclient_load_binary(bz_dclient* dc, const uint8_t*, size_t) {
-  // The kernels are part of this library (fatbin, sm_100a); there is no image to load.
-  return dc ? BZ_OK : fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null DriverClient");
-}
-
-extern "C" int32_t bz_dclient_device_info(bz_dclient* dc, char* name, size_t name_len, uint64_t* hbm_total, uint64_t* hbm_free) {
-  int32_t rc = dc_select(dc);
-  if (rc) return rc;
-  cudaDeviceProp prop;
-  CUDA_TRY(BZ_ERR_READ, cudaGetDeviceProperties(&prop, dc->device));
-  if (name && name_len) { strncpy(name, prop.name, name_len - 1); name[name_len - 1] = 0; }
-  size_t f = 0, t = 0;
-  CUDA_TRY(BZ_ERR_READ, cudaMemGetInfo(&f, &t));
-  if (hbm_total) *hbm_total = t;
-  if (hbm_free) *hbm_free = f;
-  return BZ_OK;
-}
-
-extern "C" int32_t bz_host_alloc(size_t bytes, void** out) {
-  if (!out) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "out is null");
-  CUDA_TRY(BZ_ERR_NO_DEVICE, cudaHostAlloc(out, bytes, cudaHostAllocDefault));
-  return BZ_OK;
-}
-extern "C" int32_t bz_host_free(void* p) {
-  if (p) CUDA_TRY(BZ_ERR_UNKNOWN, cudaFreeHost(p));
-  return BZ_OK;
-}
 
 // ------------------------------------------------------------------------------------ MSM planning
 static const CurveOps* ops_for(int curve) {
@@ -250,79 +81,6 @@ static int plan_windows(const uint32_t smax[8], int sbits, int c, DigitConst& dc
     }
   }
 }
-
-static const int RESULT_SLOTS = 16;     // max tasks in flight per client
-static const int RESULT_SLOT_BYTES = 272;   // 3*48 result bytes + error word, 16-byte aligned
-
-struct MsmTaskResult {
-  std::vector<uint8_t> bytes;   // filled from the pinned slot when the event has completed
-  uint32_t label = 0;
-  cudaEvent_t done = nullptr;
-  uint8_t* host_slot = nullptr;   // pinned (slot of bz_msm::pinned)
-  int* host_err = nullptr;        // pinned
-  bool collected = false;
-  int32_t status = BZ_OK;
-};
-
-struct bz_msm {
-  bz_dclient* dc = nullptr;
-  const CurveOps* ops = nullptr;
-  int curve = 0, mem_type = BZ_MEM_DMA, factor = 1;
-  // "registers" of the reference core
-  uint32_t nof_elements = 0;
-  bool hbm_mode = false;
-  uint64_t hbm_addr = 0, hbm_off = 0;
-  uint32_t next_label = 0, last_label = 0;
-  int forced_c = 0;
-  // task state machine
-  int pending_tasks = 0;     // start_process() calls not yet matched with data
-  bool data_ready = false;   // set_data() arrived, not yet consumed by a task
-  uint64_t data_M = 0;
-  std::deque<MsmTaskResult> results;
-  // device state
-  MsmPlan plan{};
-  bool have_plan = false;
-  MsmWorkspace ws{};
-  std::vector<void*> ws_allocs;
-  void* table = nullptr;
-  uint64_t table_cap = 0, table_n = 0, table_addr = ~0ull, table_epoch = 0;
-  bool table_from_arena = false;
-  // window-merged table (SURVEY 8(a) "HBM-resident precomputed points"): entry w*n + i = 2^(c w) * P_i.  Built on
-  // the second MSM over an unchanged resident point set (precomp_mode 1), immediately (2) or never (0).
-  void* wtable = nullptr;
-  size_t wtable_bytes = 0;
-  uint64_t wtable_n = 0, wtable_addr = ~0ull, wtable_epoch = 0;
-  int wtable_c = 0, wtable_levels = 0;
-  int precomp_mode = 1;
-  int raw_result = 0;            // bz_msm_set_raw_result
-  bool precomp_failed = false;   // allocation failed for this point set: stay on the plain table
-  uint64_t table_uses = 0;       // MSMs launched on the current arena table
-  uint8_t* comb_dev = nullptr;   // scratch of bz_msm_combine_results
-  size_t comb_cap = 0;
-  uint8_t* dma_points = nullptr;
-  size_t dma_points_cap = 0;
-  // DMA mode: the points travel on the copy stream BEHIND the scalars, so digits + sort of the task run while
-  // the (larger) point copy is still in flight; the table is built on the work stream once they have landed
-  bool table_pending = false;
-  uint64_t table_pending_n = 0;
-  cudaEvent_t ev_points_copied = nullptr, ev_points_consumed = nullptr;
-  bool points_consumed_valid = false;
-  // scalar ingest: two staging buffers filled on a dedicated copy stream, so the H2D of task k+1
-  // overlaps the kernels of task k (the reference's task queue allows exactly that pipelining)
-  uint32_t* scalars_dev[2] = {nullptr, nullptr};
-  size_t scalars_cap[2] = {0, 0};
-  cudaStream_t copy_stream = nullptr;
-  cudaEvent_t ev_copied[2] = {nullptr, nullptr};     // copy stream: staging buffer b is filled
-  cudaEvent_t ev_consumed[2] = {nullptr, nullptr};   // work stream: k_digits has read staging buffer b
-  bool consumed_valid[2] = {false, false};
-  int stage_next = 0, stage_cur = -1;
-  const uint32_t* scalars_src = nullptr;   // where the pending task reads its scalars from
-  uint8_t* pinned = nullptr;   // RESULT_SLOTS result slots
-  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // start, sorted, acc begin, acc end, done
-  float last_ms[4] = {0, 0, 0, 0};
-  bool timed = false;
-  std::mutex mu;
-};
 
 static void wtable_free(bz_msm* m) {
   if (m->wtable) cudaFree(m->wtable);
@@ -538,9 +296,8 @@ static int32_t make_plan(bz_msm* m, uint64_t M, int words_per_scalar, bool merge
   return BZ_OK;
 }
 
-// ------------------------------------------------------------------------------------ MSM client
-extern "C" int32_t bz_msm_new(bz_dclient* dc, int32_t curve, int32_t mem_type, int32_t is_precompute, bz_msm** out) {
-  if (!out) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "out is null");
+// ------------------------------------------------------------------------------------ MSM client (leaf)
+int32_t bz::leaf_new(bz_dclient* dc, int32_t curve, int32_t mem_type, int32_t is_precompute, bz_msm** out) {
   *out = nullptr;
   int32_t rc = dc_select(dc);
   if (rc) return rc;
@@ -554,7 +311,7 @@ extern "C" int32_t bz_msm_new(bz_dclient* dc, int32_t curve, int32_t mem_type, i
   m->mem_type = mem_type;
   m->factor = is_precompute ? 8 : 1;   // PRECOMPUTE_FACTOR / PRECOMPUTE_FACTOR_BASE, msm_api.rs:39-40
   if (const char* e = getenv("BZ_MSM_PRECOMP")) { int v = atoi(e); if (v >= 0 && v <= 2) m->precomp_mode = v; }
-  for (auto& e : m->ev) cudaEventCreate(&e);
+  for (auto& slot : m->tev) for (auto& e : slot) cudaEventCreate(&e);
   cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking);
   for (int b = 0; b < 2; b++) {
     cudaEventCreateWithFlags(&m->ev_copied[b], cudaEventDisableTiming);
@@ -562,8 +319,8 @@ extern "C" int32_t bz_msm_new(bz_dclient* dc, int32_t curve, int32_t mem_type, i
   }
   cudaEventCreateWithFlags(&m->ev_points_copied, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&m->ev_points_consumed, cudaEventDisableTiming);
-  if (cudaHostAlloc((void**)&m->pinned, (size_t)RESULT_SLOTS * RESULT_SLOT_BYTES, cudaHostAllocDefault) != cudaSuccess) {
-    delete m;
+  if (cudaHostAlloc((void**)&m->pinned, (size_t)RESULT_SLOTS * RESULT_SLOT_BYTES, cudaHostAllocPortable) != cudaSuccess) {
+    leaf_free(m);
     return fail(BZ_ERR_NO_DEVICE, "pinned allocation failed");
   }
   *out = m;
@@ -575,10 +332,11 @@ static void result_release(MsmTaskResult& r) {
   r.done = nullptr; r.host_slot = nullptr; r.host_err = nullptr;
 }
 
-extern "C" int32_t bz_msm_free(bz_msm* m) {
+int32_t bz::leaf_free(bz_msm* m) {
   if (!m) return BZ_OK;
   cudaSetDevice(m->dc->device);
   cudaStreamSynchronize(m->dc->stream);
+  if (m->copy_stream) cudaStreamSynchronize(m->copy_stream);
   for (auto& r : m->results) result_release(r);
   ws_free(m);
   if (m->table) cudaFree(m->table);
@@ -594,36 +352,13 @@ extern "C" int32_t bz_msm_free(bz_msm* m) {
   if (m->ev_points_consumed) cudaEventDestroy(m->ev_points_consumed);
   if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
   if (m->pinned) cudaFreeHost(m->pinned);
-  for (auto& e : m->ev) if (e) cudaEventDestroy(e);
+  for (auto& slot : m->tev) for (auto& e : slot) if (e) cudaEventDestroy(e);
+  for (auto& e : m->ev_part) if (e) cudaEventDestroy(e);
   delete m;
   return BZ_OK;
 }
 
-extern "C" int32_t bz_msm_sizes(bz_msm* m, uint32_t* scalar_size, uint32_t* point_size, uint32_t* result_point_size, uint32_t* precompute_factor) {
-  if (!m) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null MSMClient");
-  if (scalar_size) *scalar_size = 32;
-  if (point_size) *point_size = 2 * m->ops->fq_bytes;
-  if (result_point_size) *result_point_size = 3 * m->ops->fq_bytes;
-  if (precompute_factor) *precompute_factor = m->factor;
-  return BZ_OK;
-}
-
-extern "C" int32_t bz_msm_loaded_binary_parameters(bz_msm* m, uint32_t out[2]) {
-  if (!m || !out) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null argument");
-  // [0] image id, [1] image parameters.  The reference decodes [1] as
-  // reverse_bits().to_be_bytes() unpacked msb0 (msm_api.rs:333-354): after the reversal, LSB-first:
-  // bits 0..3 placeholder, 4..7 #segments, 8..15 bucket addr width, 16..19 #ec adders,
-  // 20..27 curve, 28..31 is_stub.  We synthesise: segments = 1, addr width = current c-1 (or 0),
-  // ec adders = 0xF (saturated: 148 SMs do not fit 4 bits), curve code, is_stub = 0.
-  uint32_t c = m->have_plan ? (uint32_t)(m->plan.c - 1) : 0;
-  uint32_t word = (1u << 4) | ((c & 0xff) << 8) | (0xFu << 16) | (((uint32_t)m->curve & 0xff) << 20);
-  out[0] = 0xB2000000u | (uint32_t)m->curve;
-  out[1] = word;
-  return BZ_OK;
-}
-
-extern "C" int32_t bz_msm_initialize(bz_msm* m, uint32_t nof_elements, int32_t has_hbm_addr, uint64_t hbm_addr, uint64_t hbm_offset) {
-  if (!m) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null MSMClient");
+int32_t bz::leaf_initialize(bz_msm* m, uint32_t nof_elements, int32_t has_hbm_addr, uint64_t hbm_addr, uint64_t hbm_offset) {
   std::lock_guard<std::mutex> lk(m->mu);
   if (m->mem_type == BZ_MEM_DMA && !has_hbm_addr) {
     m->hbm_mode = false;                      // BASES_SOURCE = 0, msm_api.rs:75-81
@@ -642,8 +377,7 @@ extern "C" int32_t bz_msm_initialize(bz_msm* m, uint32_t nof_elements, int32_t h
 // make sure the window-merged table matches the current plan (c, Wd) and the resident point set
 static int32_t ensure_wtable(bz_msm* m, uint64_t n) {
   const MsmPlan& p = m->plan;
-  if (m->wtable && m->wtable_n == n && m->wtable_c == p.c && m->wtable_levels == p.Wd && m->wtable_addr == m->table_addr &&
-      m->wtable_epoch == m->table_epoch)
+  if (m->wtable && m->wtable_n == n && m->wtable_c == p.c && m->wtable_levels == p.Wd && m->wtable_gen == m->table_gen)
     return BZ_OK;
   const size_t bytes = (size_t)p.Wd * n * m->ops->affine_bytes;
   if (m->wtable_bytes < bytes) {
@@ -656,18 +390,39 @@ static int32_t ensure_wtable(bz_msm* m, uint64_t n) {
     m->wtable_bytes = bytes;
   }
   cudaStream_t st = m->dc->stream;
+  nvtxRangePushA("blaze_b200: window-merged table build");
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  cudaEventRecord(e0, st);
   CUDA_TRY(BZ_ERR_WRITE, cudaMemcpyAsync(m->wtable, m->table, n * m->ops->affine_bytes, cudaMemcpyDeviceToDevice, st));
   m->ops->build_wtable(m->wtable, n, p.Wd, p.c, st);
+  cudaEventRecord(e1, st);
   CUDA_TRY(BZ_ERR_UNKNOWN, cudaGetLastError());
+  // one-off and long (seconds at 2^26): wait for it here so that its duration can be reported (bz_msm_table_build_ms)
+  cudaEventSynchronize(e1);
+  cudaEventElapsedTime(&m->wtable_build_ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  nvtxRangePop();
   m->wtable_n = n;
   m->wtable_c = p.c;
   m->wtable_levels = p.Wd;
-  m->wtable_addr = m->table_addr;
-  m->wtable_epoch = m->table_epoch;
+  m->wtable_gen = m->table_gen;
   return BZ_OK;
 }
 
 static int32_t build_table(bz_msm* m, const uint8_t* raw_dev, uint64_t n_points);
+
+int32_t bz::leaf_comb_reserve(bz_msm* m, size_t bytes) {
+  if (m->comb_cap >= bytes) return BZ_OK;
+  if (m->comb_dev) cudaFree(m->comb_dev);   // cudaFree waits for outstanding work
+  m->comb_dev = nullptr;
+  m->comb_cap = 0;
+  CUDA_TRY(BZ_ERR_WRITE, cudaMalloc((void**)&m->comb_dev, bytes));
+  m->comb_cap = bytes;
+  return BZ_OK;
+}
 
 // enqueue the whole pipeline for one task on the client's stream
 static int32_t launch_task(bz_msm* m) {
@@ -675,6 +430,8 @@ static int32_t launch_task(bz_msm* m) {
   const uint64_t M = m->data_M;
   const int wps = m->factor == 8 ? 1 : 8;
   cudaStream_t st = dc->stream;
+  // nothing is touched before we know the task can be queued (a refused task must not burn a label or a slot)
+  if ((int)m->results.size() >= RESULT_SLOTS) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "more than %d results pending; pop them with result()", RESULT_SLOTS);
   // window-merged table: only for a resident (arena) point set with full-width scalars, and by default only once
   // the same point set is used a second time (building it costs about as much as a dozen plain MSMs)
   bool merged = false;
@@ -692,19 +449,24 @@ static int32_t launch_task(bz_msm* m) {
     rc = make_plan(m, M, wps, false);
     if (rc) return rc;
   }
-  if (m->table_from_arena) m->table_uses++;
+  const size_t rs = 3 * (size_t)m->ops->fq_bytes;
+  const bool ranked = dc->comm != nullptr && dc->world > 1;
+  if (ranked) { rc = leaf_comb_reserve(m, rs * (dc->world + 1)); if (rc) return rc; }
   MsmTaskResult r;
+  CUDA_TRY(BZ_ERR_UNKNOWN, cudaEventCreateWithFlags(&r.done, cudaEventBlockingSync | cudaEventDisableTiming));
+  if (m->table_from_arena) m->table_uses++;
   r.label = m->next_label++;
   m->last_label = r.label;
-  CUDA_TRY(BZ_ERR_UNKNOWN, cudaEventCreateWithFlags(&r.done, cudaEventBlockingSync | cudaEventDisableTiming));
-  if ((int)m->results.size() >= RESULT_SLOTS) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "more than %d results pending; pop them with result()", RESULT_SLOTS);
-  r.host_slot = m->pinned + (size_t)(r.label % RESULT_SLOTS) * RESULT_SLOT_BYTES;
+  r.slot = (int)(r.label % RESULT_SLOTS);   // labels in flight are consecutive and at most RESULT_SLOTS: slots are distinct
+  r.host_slot = m->pinned + (size_t)r.slot * RESULT_SLOT_BYTES;
   r.host_err = reinterpret_cast<int*>(r.host_slot + 256);
+  cudaEvent_t* ev = m->tev[r.slot];
+  nvtxRangePushA("blaze_b200: MSM task enqueue");
   CUDA_TRY(BZ_ERR_UNKNOWN, cudaMemsetAsync(m->ws.err, 0, 4, st));
-  m->ws.ev_acc0 = m->ev[2];
-  m->ws.ev_acc1 = m->ev[3];
+  m->ws.ev_acc0 = ev[2];
+  m->ws.ev_acc1 = ev[3];
   if (m->stage_cur >= 0) CUDA_TRY(BZ_ERR_UNKNOWN, cudaStreamWaitEvent(st, m->ev_copied[m->stage_cur], 0));
-  cudaEventRecord(m->ev[0], st);
+  cudaEventRecord(ev[0], st);
   launch_msm_sort(m->plan, m->ws, m->scalars_src, st);
   if (m->stage_cur >= 0) {   // k_digits (the only reader of the staging buffer) is queued: mark it consumed
     cudaEventRecord(m->ev_consumed[m->stage_cur], st);
@@ -718,28 +480,43 @@ static int32_t launch_task(bz_msm* m) {
     m->points_consumed_valid = true;
     m->table_pending = false;
   }
-  cudaEventRecord(m->ev[1], st);
-  m->plan.raw_result = m->raw_result;
+  cudaEventRecord(ev[1], st);
+  m->plan.raw_result = (m->raw_result || ranked) ? 1 : 0;
   m->ops->bucket_phase(m->plan, m->ws, merged ? m->wtable : m->table, st);
-  cudaEventRecord(m->ev[4], st);
-  m->timed = true;
   CUDA_TRY(BZ_ERR_UNKNOWN, cudaGetLastError());
-  CUDA_TRY(BZ_ERR_READ, cudaMemcpyAsync(r.host_slot, m->ws.result, 3 * m->ops->fq_bytes, cudaMemcpyDeviceToHost, st));
+  const uint8_t* final_rec = m->ws.result;
+  if (ranked) {
+    // final exchange of the point-sharded MSM, device side: all-gather of the ranks' projective records straight into
+    // the combine kernel on the same stream (no host bounce); every rank ends with the same normalised (or raw) sum
+    rc = comm_allgather(dc, m->ws.result, m->comb_dev, rs, st);
+    if (rc) return rc;
+    m->ops->combine_results(m->comb_dev, dc->world, m->comb_dev + rs * dc->world, m->raw_result, st);
+    g_kernel_launches += 1;
+    final_rec = m->comb_dev + rs * dc->world;
+  }
+  cudaEventRecord(ev[4], st);
+  CUDA_TRY(BZ_ERR_UNKNOWN, cudaGetLastError());
+  CUDA_TRY(BZ_ERR_READ, cudaMemcpyAsync(r.host_slot, final_rec, rs, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(BZ_ERR_READ, cudaMemcpyAsync(r.host_err, m->ws.err, 4, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(BZ_ERR_UNKNOWN, cudaEventRecord(r.done, st));
+  nvtxRangePop();
   m->results.push_back(r);
   m->pending_tasks--;
   m->data_ready = false;
+  m->launched++;
   return BZ_OK;
 }
 
-extern "C" int32_t bz_msm_start_process(bz_msm* m) {
-  if (!m) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null MSMClient");
+int32_t bz::leaf_start_process(bz_msm* m) {
   int32_t rc = dc_select(m->dc);
   if (rc) return rc;
   std::lock_guard<std::mutex> lk(m->mu);
   m->pending_tasks++;                          // PUSH_MSM_TASK_TO_QUEUE, msm_api.rs:113-120
-  if (m->data_ready) return launch_task(m);
+  if (m->data_ready) {
+    rc = launch_task(m);
+    if (rc) m->pending_tasks--;                // the refused task is not left queued
+    return rc;
+  }
   return BZ_OK;
 }
 
@@ -755,23 +532,29 @@ static int32_t build_table(bz_msm* m, const uint8_t* raw_dev, uint64_t n_points)
   m->ops->points_to_mont(raw_dev, m->table, n_points, m->dc->stream);
   CUDA_TRY(BZ_ERR_UNKNOWN, cudaGetLastError());
   m->table_n = n_points;
+  m->table_gen++;
   return BZ_OK;
 }
 
 static int32_t ensure_arena_table(bz_msm* m, uint64_t addr, uint64_t n_points) {
   bz_dclient* dc = m->dc;
-  if (m->table_from_arena && m->table_addr == addr && m->table_n == n_points && m->table_epoch == dc->epoch) return BZ_OK;
-  uint64_t bytes = n_points * 2ull * m->ops->fq_bytes;
+  const uint64_t bytes = n_points * 2ull * m->ops->fq_bytes;
   if (addr & 15) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "hbm point address must be 16-byte aligned");
-  {
-    std::lock_guard<std::mutex> lk(dc->mu);
-    int32_t rc = arena_reserve(dc, addr + bytes);   // unwritten HBM reads as zeros = identity padding
-    if (rc) return rc;
+  if (addr + bytes < addr) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "hbm point range overflows");
+  // the card lock is held across the table build: nothing can write the range between the check and the launch, and
+  // the address space never moves (virtual reservation), so the kernel's pointer stays valid after the unlock
+  std::lock_guard<std::mutex> lk(dc->mu);
+  if (m->table_from_arena && m->table_addr == addr && m->table_n == n_points &&
+      !arena_dirty_since(dc, m->table_epoch, addr, addr + bytes)) {
+    m->table_epoch = dc->epoch;   // nothing overlapping was written: keep the window of the write log short
+    return BZ_OK;
   }
+  int32_t rc = arena_map(dc, addr, addr + bytes);   // unwritten HBM reads as zeros = identity padding
+  if (rc) return rc;
   wtable_free(m);   // stale: derived from the previous point set
   m->precomp_failed = false;
   m->table_uses = 0;
-  int32_t rc = build_table(m, dc->arena + addr, n_points);
+  rc = build_table(m, dc->arena + addr, n_points);
   if (rc) return rc;
   m->table_from_arena = true;
   m->table_addr = addr;
@@ -800,9 +583,17 @@ static int32_t stage_scalars(bz_msm* m, const uint8_t* scalars, size_t len) {
   return BZ_OK;
 }
 
-static int32_t set_data_common(bz_msm* m, const uint8_t* points, size_t points_len, const uint8_t* scalars_host,
-                               uint64_t scalars_dev_ptr, size_t scalars_len, uint32_t nof_elements,
-                               int32_t has_hbm_addr, uint64_t hbm_addr, uint64_t hbm_offset) {
+int32_t bz::leaf_sync_copies(bz_msm* m) {
+  int32_t rc = dc_select(m->dc);
+  if (rc) return rc;
+  cudaError_t ce = cudaStreamSynchronize(m->copy_stream);
+  if (ce != cudaSuccess) return fail(BZ_ERR_WRITE, "host-to-device copy failed: %s", cudaGetErrorString(ce));
+  return BZ_OK;
+}
+
+int32_t bz::leaf_set_data(bz_msm* m, const uint8_t* points, size_t points_len, const uint8_t* scalars_host,
+                          uint64_t scalars_dev_ptr, size_t scalars_len, uint32_t nof_elements, int32_t has_hbm_addr,
+                          uint64_t hbm_addr, uint64_t hbm_offset, bool sync_host) {
   int32_t rc = dc_select(m->dc);
   if (rc) return rc;
   std::lock_guard<std::mutex> lk(m->mu);
@@ -815,7 +606,6 @@ static int32_t set_data_common(bz_msm* m, const uint8_t* points, size_t points_l
   if (!points && !has_hbm_addr) return BZ_OK;   // (None, None): the reference silently does nothing (msm_api.rs:163-216)
   const uint64_t npts = n * m->factor;
   if (npts >= (1ull << 31)) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "too many points");
-  // a new input replaces a previous un-consumed one only after the stream has drained it
   bool dma_points_now = false;
   if (points && !has_hbm_addr) {
     // DMA mode: points streamed with the call (msm_api.rs:175-202)
@@ -836,6 +626,9 @@ static int32_t set_data_common(bz_msm* m, const uint8_t* points, size_t points_l
       if (rc) return rc;
       m->hbm_mode = true; m->hbm_addr = hbm_addr; m->hbm_off = hbm_offset;
     }
+    // an HBM-mode input REPLACES a streamed (DMA) point set that no task has consumed yet: its deferred table build
+    // must not run over the table derived from HBM below
+    m->table_pending = false;
     rc = ensure_arena_table(m, a, npts);
     if (rc) return rc;
   }
@@ -860,26 +653,11 @@ static int32_t set_data_common(bz_msm* m, const uint8_t* points, size_t points_l
   if (m->pending_tasks > 0) rc = launch_task(m);
   // the caller may drop its buffers when we return (move-in semantics): block the HOST on the copy stream only --
   // the work stream keeps running (the previous task, or this task's digits + sort while the points still travel)
-  if (scalars_host || dma_points_now) {
+  if (sync_host && (scalars_host || dma_points_now)) {
     cudaError_t ce = cudaStreamSynchronize(m->copy_stream);
     if (ce != cudaSuccess && rc == BZ_OK) rc = fail(BZ_ERR_WRITE, "host-to-device copy failed: %s", cudaGetErrorString(ce));
   }
   return rc;
-}
-
-extern "C" int32_t bz_msm_set_data(bz_msm* m, const uint8_t* points, size_t points_len, const uint8_t* scalars, size_t scalars_len,
-                                   uint32_t nof_elements, int32_t has_hbm_addr, uint64_t hbm_addr, uint64_t hbm_offset) {
-  if (!m) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null MSMClient");
-  if (!scalars) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null scalars");
-  return set_data_common(m, points, points_len, scalars, 0, scalars_len, nof_elements, has_hbm_addr, hbm_addr, hbm_offset);
-}
-
-extern "C" int32_t bz_msm_set_scalars_device(bz_msm* m, uint64_t scalars_dev_ptr, uint32_t nof_elements, int32_t has_hbm_addr,
-                                             uint64_t hbm_addr, uint64_t hbm_offset) {
-  if (!m) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null MSMClient");
-  if (!scalars_dev_ptr || (scalars_dev_ptr & 15)) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "device scalar pointer must be 16-byte aligned");
-  if (!has_hbm_addr) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "device scalars need HBM-resident points");
-  return set_data_common(m, nullptr, 0, nullptr, scalars_dev_ptr, (size_t)nof_elements * 32, nof_elements, has_hbm_addr, hbm_addr, hbm_offset);
 }
 
 static int32_t collect(bz_msm* m, MsmTaskResult& r) {
@@ -889,22 +667,23 @@ static int32_t collect(bz_msm* m, MsmTaskResult& r) {
   int err = *r.host_err;
   r.status = err == BZ_ERR_NONE ? BZ_OK : BZ_ERR_INVALID_PRIMITIVE_PARAM;
   r.collected = true;
-  if (m->timed) {
+  {
+    cudaEvent_t* ev = m->tev[r.slot];
     float a = 0, b = 0, k = 0;
-    cudaEventElapsedTime(&a, m->ev[0], m->ev[4]);
-    cudaEventElapsedTime(&b, m->ev[0], m->ev[1]);
-    cudaEventElapsedTime(&k, m->ev[2], m->ev[3]);
+    cudaEventElapsedTime(&a, ev[0], ev[4]);
+    cudaEventElapsedTime(&b, ev[0], ev[1]);
+    cudaEventElapsedTime(&k, ev[2], ev[3]);
     m->last_ms[0] = a;
     m->last_ms[1] = b;
-    m->last_ms[2] = k;           // k_accumulate alone
-    m->last_ms[3] = a - b - k;   // memset + merge + reduce + finish
+    m->last_ms[2] = k;           // bucket accumulation kernel(s) alone
+    m->last_ms[3] = a - b - k;   // memset + merge + reduce + finish (+ exchange)
+    m->tasks_done++;
   }
   if (r.status) return fail(r.status, "device flagged a non-canonical scalar (>= r)");
   return BZ_OK;
 }
 
-extern "C" int32_t bz_msm_wait_result(bz_msm* m) {
-  if (!m) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null MSMClient");
+int32_t bz::leaf_wait_result(bz_msm* m) {
   int32_t rc = dc_select(m->dc);
   if (rc) return rc;
   std::lock_guard<std::mutex> lk(m->mu);
@@ -912,18 +691,17 @@ extern "C" int32_t bz_msm_wait_result(bz_msm* m) {
   return collect(m, m->results.front());
 }
 
-extern "C" int32_t bz_msm_result(bz_msm* m, uint8_t* out, size_t out_len, uint32_t* result_label) {
-  if (!m || !out) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null argument");
+int32_t bz::leaf_result(bz_msm* m, uint8_t* out, size_t out_len, uint32_t* result_label) {
   int32_t rc = dc_select(m->dc);
   if (rc) return rc;
   std::lock_guard<std::mutex> lk(m->mu);
   if (m->results.empty()) return fail(BZ_ERR_NO_RESULT, "result queue is empty");
   size_t need = 3 * (size_t)m->ops->fq_bytes;
-  if (out_len < need) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "result buffer too small (%zu < %zu)", out_len, need);
+  if (out && out_len < need) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "result buffer too small (%zu < %zu)", out_len, need);
   MsmTaskResult& r = m->results.front();
   rc = collect(m, r);
   if (rc == BZ_OK) {
-    memcpy(out, r.bytes.data(), need);
+    if (out) memcpy(out, r.bytes.data(), need);
     if (result_label) *result_label = r.label;
   }
   result_release(r);
@@ -931,24 +709,7 @@ extern "C" int32_t bz_msm_result(bz_msm* m, uint8_t* out, size_t out_len, uint32
   return rc;
 }
 
-extern "C" int32_t bz_msm_task_label(bz_msm* m, uint32_t* label) {
-  if (!m || !label) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null argument");
-  *label = m->last_label;
-  return BZ_OK;
-}
-extern "C" int32_t bz_msm_nof_elements(bz_msm* m, uint32_t* n) {
-  if (!m || !n) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null argument");
-  *n = m->nof_elements;
-  return BZ_OK;
-}
-extern "C" int32_t bz_msm_is_msm_engine_ready(bz_msm* m, uint32_t* ready) {
-  if (!m || !ready) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null argument");
-  *ready = 1;
-  return BZ_OK;
-}
-
-extern "C" int32_t bz_msm_load_data_to_hbm(bz_msm* m, const uint8_t* points, size_t len, uint64_t addr, uint64_t offset) {
-  if (!m) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null MSMClient");
+int32_t bz::leaf_load_data_to_hbm(bz_msm* m, const uint8_t* points, size_t len, uint64_t addr, uint64_t offset) {
   {
     std::lock_guard<std::mutex> lk(m->mu);
     m->hbm_mode = true;                        // BASES_SOURCE = 1 + start address, msm_api.rs:299-311
@@ -956,87 +717,34 @@ extern "C" int32_t bz_msm_load_data_to_hbm(bz_msm* m, const uint8_t* points, siz
   }
   return bz_dclient_dma_write(m->dc, addr, offset, points, len);
 }
-extern "C" int32_t bz_msm_get_data_from_hbm(bz_msm* m, uint8_t* out, size_t len, uint64_t addr, uint64_t offset) {
-  if (!m) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null MSMClient");
-  return bz_dclient_dma_read(m->dc, addr, offset, out, len);
-}
 
-extern "C" int32_t bz_msm_phase_times(bz_msm* m, float ms[4]) {
-  if (!m || !ms) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null argument");
+int32_t bz::leaf_phase_times(bz_msm* m, float ms[4]) {
+  std::lock_guard<std::mutex> lk(m->mu);
   memcpy(ms, m->last_ms, sizeof(m->last_ms));
   return BZ_OK;
 }
-extern "C" int32_t bz_msm_set_window_bits(bz_msm* m, int32_t c) {
-  if (!m) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null MSMClient");
-  if (c != 0 && (c < 4 || c > 26)) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "window bits must be 0 or in [4, 26]");
-  std::lock_guard<std::mutex> lk(m->mu);
-  m->forced_c = c;
-  return BZ_OK;
-}
-extern "C" int32_t bz_msm_set_precompute(bz_msm* m, int32_t mode) {
-  if (!m) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null MSMClient");
-  if (mode < 0 || mode > 2) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "precompute mode must be 0 (never), 1 (on reuse) or 2 (always)");
-  std::lock_guard<std::mutex> lk(m->mu);
-  m->precomp_mode = mode;
-  m->precomp_failed = false;
-  return BZ_OK;
-}
-extern "C" int32_t bz_msm_set_raw_result(bz_msm* m, int32_t raw) {
-  if (!m) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null MSMClient");
-  std::lock_guard<std::mutex> lk(m->mu);
-  m->raw_result = raw ? 1 : 0;
-  return BZ_OK;
-}
-extern "C" int32_t bz_msm_plan_info_ex(bz_msm* m, uint32_t out[8]) {
-  if (!m || !out) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null argument");
-  memset(out, 0, 8 * sizeof(uint32_t));
-  if (!m->have_plan) return BZ_OK;
-  out[0] = m->plan.c;
-  out[1] = m->plan.Wd;        // digit windows = mixed adds per scalar
-  out[2] = m->plan.nvalues;
-  out[3] = m->plan.seg_len;
-  out[4] = m->plan.W;         // bucket sets (1 when the windows are merged)
-  out[5] = m->plan.merged;
-  out[6] = (uint32_t)(m->wtable_bytes >> 20);   // MiB held by the window-merged table
-  out[7] = m->plan.fb | (m->plan.rest << 8) | (m->plan.nlev << 16);
-  return BZ_OK;
-}
-extern "C" int32_t bz_msm_plan_info(bz_msm* m, uint32_t out[4]) {
-  if (!m || !out) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null argument");
-  out[0] = m->have_plan ? m->plan.c : 0;
-  out[1] = m->have_plan ? m->plan.Wd : 0;
-  out[2] = m->have_plan ? m->plan.nvalues : 0;
-  out[3] = m->have_plan ? m->plan.seg_len : 0;
-  return BZ_OK;
-}
 
-extern "C" int32_t bz_msm_combine_results(bz_msm* m, const uint8_t* records, int32_t n, uint8_t* out, size_t out_len) {
-  if (!m || !records || !out || n <= 0) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "bad argument");
+int32_t bz::leaf_combine_results(bz_msm* m, const uint8_t* records, int32_t n, uint8_t* out, size_t out_len) {
   int32_t rc = dc_select(m->dc);
   if (rc) return rc;
   size_t rs = 3 * (size_t)m->ops->fq_bytes;
   if (out_len < rs) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "result buffer too small");
   std::lock_guard<std::mutex> lk(m->mu);
-  if (m->comb_cap < rs * (n + 1)) {   // small scratch kept across calls (no cudaMalloc / cudaFree per step)
-    if (m->comb_dev) cudaFree(m->comb_dev);
-    m->comb_dev = nullptr;
-    m->comb_cap = 0;
-    CUDA_TRY(BZ_ERR_WRITE, cudaMalloc((void**)&m->comb_dev, rs * (n + 1)));
-    m->comb_cap = rs * (n + 1);
-  }
+  rc = leaf_comb_reserve(m, rs * (n + 1));   // small scratch kept across calls (no cudaMalloc / cudaFree per step)
+  if (rc) return rc;
   uint8_t* d = m->comb_dev;
   cudaStream_t st = m->dc->stream;
   cudaMemcpyAsync(d, records, rs * n, cudaMemcpyHostToDevice, st);
-  m->ops->combine_results(d, n, d + rs * n, st);
+  m->ops->combine_results(d, n, d + rs * n, 0, st);
+  g_kernel_launches += 1;
   cudaMemcpyAsync(out, d + rs * n, rs, cudaMemcpyDeviceToHost, st);
   cudaError_t e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) return fail(BZ_ERR_UNKNOWN, "combine failed: %s", cudaGetErrorString(e));
   return BZ_OK;
 }
 
-extern "C" int32_t bz_msm_generate_chain_points(bz_msm* m, const uint8_t* p0q, size_t p0q_len, uint64_t first, uint64_t n,
-                                                uint64_t addr, uint64_t offset) {
-  if (!m || !p0q) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null argument");
+int32_t bz::leaf_generate_chain_points(bz_msm* m, const uint8_t* p0q, size_t p0q_len, uint64_t first, uint64_t n,
+                                       uint64_t addr, uint64_t offset) {
   int32_t rc = dc_select(m->dc);
   if (rc) return rc;
   size_t ps = 2 * (size_t)m->ops->fq_bytes;
@@ -1046,7 +754,7 @@ extern "C" int32_t bz_msm_generate_chain_points(bz_msm* m, const uint8_t* p0q, s
   uint64_t a = addr + offset;
   if (a & 15) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "address must be 16-byte aligned");
   std::lock_guard<std::mutex> lk(dc->mu);
-  rc = arena_reserve(dc, a + n * ps);
+  rc = arena_map(dc, a, a + n * ps);
   if (rc) return rc;
   uint8_t* d = nullptr;
   CUDA_TRY(BZ_ERR_WRITE, cudaMalloc((void**)&d, 2 * ps));
@@ -1054,25 +762,7 @@ extern "C" int32_t bz_msm_generate_chain_points(bz_msm* m, const uint8_t* p0q, s
   m->ops->gen_chain_points(d, first, n, dc->arena + a, dc->stream);
   cudaError_t e = cudaStreamSynchronize(dc->stream);
   cudaFree(d);
-  dc->epoch++;
+  arena_note_write(dc, a, a + n * ps);
   if (e != cudaSuccess) return fail(BZ_ERR_UNKNOWN, "generator failed: %s", cudaGetErrorString(e));
-  return BZ_OK;
-}
-
-extern "C" int32_t bz_msm_field_selftest(bz_msm* m, const uint8_t* a, const uint8_t* b, uint8_t* out, int32_t n, int32_t op) {
-  if (!m || !a || !b || !out || n <= 0) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "bad argument");
-  int32_t rc = dc_select(m->dc);
-  if (rc) return rc;
-  size_t bytes = (size_t)n * m->ops->fq_bytes;
-  uint8_t* d = nullptr;
-  CUDA_TRY(BZ_ERR_WRITE, cudaMalloc((void**)&d, 3 * bytes));
-  cudaStream_t st = m->dc->stream;
-  cudaMemcpyAsync(d, a, bytes, cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(d + bytes, b, bytes, cudaMemcpyHostToDevice, st);
-  m->ops->field_selftest(d, d + bytes, d + 2 * bytes, n, op, st);
-  cudaMemcpyAsync(out, d + 2 * bytes, bytes, cudaMemcpyDeviceToHost, st);
-  cudaError_t e = cudaStreamSynchronize(st);
-  cudaFree(d);
-  if (e != cudaSuccess) return fail(BZ_ERR_UNKNOWN, "selftest failed: %s", cudaGetErrorString(e));
   return BZ_OK;
 }

@@ -200,6 +200,22 @@ __global__ void __launch_bounds__(128) k_wtable_level(const AffineT<C>* __restri
   }
 }
 
+// level-major Montgomery table (entry w*n + i) -> the reference's precomputed wire format (tests/msm/mod.rs:360-380):
+// record i = level 0 .. levels-1 of point i, affine x||y canonical little-endian
+template <class C>
+__global__ void __launch_bounds__(128) k_table_to_wire(const AffineT<C>* __restrict__ table, uint64_t n, int levels,
+                                                       uint8_t* __restrict__ out) {
+  typedef dev<C> D;
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * (uint64_t)levels) return;
+  const uint64_t i = t / levels;
+  const int w = (int)(t % levels);
+  Affine<C> a = D::load_affine(table[(uint64_t)w * n + i].x);
+  uint8_t* o = out + t * (2 * C::FQ_BYTES);
+  D::store_canonical(o, a.x);
+  D::store_canonical(o + C::FQ_BYTES, a.y);
+}
+
 // ---------------------------------------------------------------------------------------------
 // bucket accumulation (the dominant kernel)
 // CTAs of 128 threads per SM.  3 (168 registers: the 12-limb curves spill ~170 B/thread around the field calls)
@@ -549,7 +565,7 @@ __global__ void k_finish(const XyzzM<C>* __restrict__ win, int W, int c, int raw
 
 // sum n canonical result records
 template <class C>
-__global__ void k_combine_results(const uint8_t* __restrict__ recs, int n, uint8_t* __restrict__ out) {
+__global__ void k_combine_results(const uint8_t* __restrict__ recs, int n, int raw, uint8_t* __restrict__ out) {
   typedef dev<C> D;
   typedef ec<C> G;
   if (blockIdx.x || threadIdx.x) return;
@@ -570,7 +586,8 @@ __global__ void k_combine_results(const uint8_t* __restrict__ recs, int n, uint8
     p.Y = ff<typename C::Fq>::mul(Y, p.ZZ);
     G::add(acc, p);
   }
-  D::store_result(out, acc);
+  if (raw) D::store_result_raw(out, acc);
+  else D::store_result(out, acc);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -723,8 +740,14 @@ struct CurveLaunch {
       g_kernel_launches += 1;
     }
   }
-  static void combine_results(const uint8_t* recs, int n, uint8_t* out, cudaStream_t st) {
-    k_combine_results<C><<<1, 32, 0, st>>>(recs, n, out);
+  static void table_to_wire(const void* table, uint64_t n, int levels, uint8_t* out, cudaStream_t st) {
+    const uint64_t total = n * (uint64_t)levels;
+    if (!total) return;
+    k_table_to_wire<C><<<(unsigned)((total + 127) / 128), 128, 0, st>>>((const AffineT<C>*)table, n, levels, out);
+    g_kernel_launches += 1;
+  }
+  static void combine_results(const uint8_t* recs, int n, uint8_t* out, int raw, cudaStream_t st) {
+    k_combine_results<C><<<1, 32, 0, st>>>(recs, n, raw, out);
   }
   static void gen_chain_points(const uint8_t* p0q, uint64_t first, uint64_t n, uint8_t* out, cudaStream_t st) {
     if (!n) return;
@@ -744,6 +767,7 @@ struct CurveLaunch {
                                &points_to_mont,
                                &bucket_phase,
                                &build_wtable,
+                               &table_to_wire,
                                &combine_results,
                                &gen_chain_points,
                                &field_selftest};

@@ -114,8 +114,10 @@ struct CurveOps {
   void (*bucket_phase)(const MsmPlan& p, const MsmWorkspace& ws, const void* table, cudaStream_t st);
   // window-merged table: level w (entries [w*n, (w+1)*n)) = 2^c * level w-1; level 0 must already be in place
   void (*build_wtable)(void* wtable, uint64_t n, int levels, int c, cudaStream_t st);
-  // sum `n` canonical result records (Z||Y||X) into one canonical record (multi-GPU combine)
-  void (*combine_results)(const uint8_t* recs, int n, uint8_t* out, cudaStream_t st);
+  // level-major table (entry w*n + i) -> wire records (levels affine points per base, canonical LE)
+  void (*table_to_wire)(const void* table, uint64_t n, int levels, uint8_t* out, cudaStream_t st);
+  // sum `n` result records (Z||Y||X, any Z) into one record: canonical (Z = 1), or left projective when raw != 0
+  void (*combine_results)(const uint8_t* recs, int n, uint8_t* out, int raw, cudaStream_t st);
   // test / bench helpers
   void (*gen_chain_points)(const uint8_t* p0q_raw, uint64_t first, uint64_t n, uint8_t* out_raw, cudaStream_t st);
   void (*field_selftest)(const uint8_t* a, const uint8_t* b, uint8_t* out, int n, int op, cudaStream_t st);

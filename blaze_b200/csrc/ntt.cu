@@ -194,6 +194,12 @@ __global__ void __launch_bounds__(256, 2) k_ntt_pass(NttPassParams P) {
       continue;
     }
     E x = nt<F>::ld(P.in + 2 * off);
+    if (P.err) {   // wire elements must be canonical (< r): the butterflies' add / sub assume it
+      cc::sub_cc(x.v[0], F::mod()[0]);
+#pragma unroll
+      for (int i = 1; i < 8; i++) cc::subc_cc(x.v[i], F::mod()[i]);
+      if (cc::subc(0u, 0u) == 0u) atomicExch(P.err, 1);   // no borrow: x >= r
+    }
     if (P.tw_sel >= 0 && r != 0) {
       uint64_t tq = P.tw_sel == 0 ? q0 : (P.tw_sel == 1 ? q1 : q2);
       if (tq != 0) {

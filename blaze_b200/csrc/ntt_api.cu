@@ -18,6 +18,7 @@
 
 #include "../../include/blaze_b200.h"
 #include "api_common.h"
+#include "client_internal.h"
 #include "ntt_internal.h"
 
 using namespace bz;
@@ -40,6 +41,8 @@ struct bz_ntt {
   cudaEvent_t done = nullptr;
   bool launched = false;
   float last_ms = 0;
+  int* err_dev = nullptr;    // device flag: a transform saw a non-canonical input element
+  int* err_host = nullptr;   // pinned copy, refreshed behind every transform
   // Copies run on their own streams so that the H2D of one slot and the D2H of the other overlap the transform
   // (the reference's double-buffer pipeline, integration_ntt.rs:103-136).  Per slot: input landed / transform
   // finished / output read -- each stream waits only for what it needs.
@@ -91,6 +94,9 @@ static int32_t ntt_new_common(bz_dclient* dc, int field, int log_n, int inverse,
   cudaEventCreateWithFlags(&t->done, cudaEventBlockingSync | cudaEventDisableTiming);
   cudaStreamCreateWithFlags(&t->h2d, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&t->d2h, cudaStreamNonBlocking);
+  cudaMalloc((void**)&t->err_dev, 16);
+  cudaHostAlloc((void**)&t->err_host, 16, cudaHostAllocPortable);
+  if (t->err_host) *t->err_host = 0;
   for (int s = 0; s < 2; s++) {
     cudaEventCreateWithFlags(&t->ev_in[s], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&t->ev_cmp[s], cudaEventDisableTiming);
@@ -118,6 +124,8 @@ extern "C" int32_t bz_ntt_free(bz_ntt* t) {
     for (cudaEvent_t e : {t->ev_in[s], t->ev_cmp[s], t->ev_out[s]}) if (e) cudaEventDestroy(e);
   for (auto& s : t->buf) for (auto& b : s) if (b) cudaFree(b);
   if (t->tab_mem) cudaFree(t->tab_mem);
+  if (t->err_dev) cudaFree(t->err_dev);
+  if (t->err_host) cudaFreeHost(t->err_host);
   for (auto p : t->tw_full) if (p) cudaFree(p);
   for (auto& e : t->ev) if (e) cudaEventDestroy(e);
   if (t->done) cudaEventDestroy(t->done);
@@ -234,9 +242,11 @@ static int32_t ntt_enqueue(bz_ntt* t, int s) {
   uint64_t Ns = 1;
   if (t->in_valid[s]) cudaStreamWaitEvent(st, t->ev_in[s], 0);     // the slot's input has landed
   if (t->out_valid[s]) cudaStreamWaitEvent(st, t->ev_out[s], 0);   // nobody is still reading the slot out
+  cudaMemsetAsync(t->err_dev, 0, 4, st);
   cudaEventRecord(t->ev[0], st);
   for (size_t p = 0; p < t->radices.size(); p++) {
     NttPassParams P = ntt_pass_params(t, p, Ns);
+    if (p == 0) P.err = t->err_dev;
     P.in = t->buf[s][t->cur[s]];
     P.out = t->buf[s][t->cur[s] ^ 1];
     P.tw_full = p < t->tw_full.size() ? t->tw_full[p] : nullptr;
@@ -246,6 +256,7 @@ static int32_t ntt_enqueue(bz_ntt* t, int s) {
     Ns <<= t->radices[p];
   }
   cudaEventRecord(t->ev[1], st);
+  cudaMemcpyAsync(t->err_host, t->err_dev, 4, cudaMemcpyDeviceToHost, st);
   cudaEventRecord(t->done, st);
   cudaEventRecord(t->ev_cmp[s], st);
   t->cmp_valid[s] = true;
@@ -277,6 +288,8 @@ extern "C" int32_t bz_ntt_wait_result(bz_ntt* t) {
   if (!t->launched) return bz_fail(BZ_ERR_NO_RESULT, "no transform in flight");
   CUDA_TRY(BZ_ERR_READ, cudaEventSynchronize(t->done));
   cudaEventElapsedTime(&t->last_ms, t->ev[0], t->ev[1]);
+  if (t->err_host && *t->err_host)
+    return bz_fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "the transformed vector held a non-canonical element (>= r); its output is undefined");
   return BZ_OK;
 }
 
@@ -339,6 +352,7 @@ struct bz_ntt_dist {
   uint4 *A = nullptr, *B = nullptr, *I = nullptr, *O = nullptr;
   uint4* peerB[NTT_MAX_PEERS] = {nullptr};
   bool peers_open = false;
+  bool use_comm = false;   // handles / barriers go through the DriverClient's communicator
   uint4* tab_mem = nullptr;
   NttTables tab{};
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -395,6 +409,26 @@ extern "C" int32_t bz_ntt_dist_new(bz_dclient* dc, int32_t field, int32_t log_si
   for (auto& e : t->ev) cudaEventCreate(&e);
   if (world == 1) { t->peerB[0] = t->B; t->peers_open = true; }
   CUDA_TRY(BZ_ERR_UNKNOWN, cudaStreamSynchronize(st));
+  if (world > 1 && dc->comm && dc->world == world && dc->rank == rank) {
+    // a ranked DriverClient: the IPC handles of the exchange buffers travel through its communicator
+    uint8_t mine[64];
+    int32_t rc2 = bz_ntt_dist_ipc_handle(t, mine);
+    uint8_t* d = nullptr;
+    std::vector<uint8_t> all((size_t)world * 64);
+    if (!rc2 && cudaMalloc((void**)&d, (size_t)(world + 1) * 64) != cudaSuccess) rc2 = bz_fail(BZ_ERR_WRITE, "device allocation failed");
+    if (!rc2) {
+      cudaMemcpyAsync(d + (size_t)world * 64, mine, 64, cudaMemcpyHostToDevice, st);
+      rc2 = comm_allgather(dc, d + (size_t)world * 64, d, 64, st);
+    }
+    if (!rc2) {
+      cudaMemcpyAsync(all.data(), d, (size_t)world * 64, cudaMemcpyDeviceToHost, st);
+      if (cudaStreamSynchronize(st) != cudaSuccess) rc2 = bz_fail(BZ_ERR_UNKNOWN, "handle exchange failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    if (d) cudaFree(d);
+    if (!rc2) rc2 = bz_ntt_dist_open_peers(t, all.data());
+    if (rc2) { bz_ntt_dist_free(t); return rc2; }
+    t->use_comm = true;
+  }
   *out = t;
   return BZ_OK;
 }
@@ -590,6 +624,25 @@ extern "C" int32_t bz_ntt_dist_step3(bz_ntt_dist* t) {
   }
   cudaEventRecord(t->ev[3], st);
   return BZ_OK;
+}
+
+// The whole transform, stream-ordered, no host synchronisation: the two cross-rank barriers (every exchange buffer is
+// free again / every rank has finished storing into every exchange buffer) are 4-byte NCCL all-reduces on the client's
+// stream.  Needs a ranked DriverClient (bz_dclient_comm_init); otherwise drive step1 / sync / barrier / step3 yourself.
+extern "C" int32_t bz_ntt_dist_run(bz_ntt_dist* t) {
+  if (!t) return bz_fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null argument");
+  int32_t rc = dc_select(t->dc);
+  if (rc) return rc;
+  cudaStream_t st = dc_stream(t->dc);
+  if (t->world > 1) {
+    if (!t->use_comm) return bz_fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "bz_ntt_dist_run needs a DriverClient with a communicator");
+    rc = comm_barrier(t->dc, st);
+    if (rc) return rc;
+  }
+  rc = bz_ntt_dist_step1(t);
+  if (rc) return rc;
+  if (t->world > 1) { rc = comm_barrier(t->dc, st); if (rc) return rc; }
+  return bz_ntt_dist_step3(t);
 }
 
 extern "C" int32_t bz_ntt_dist_plan(bz_ntt_dist* t, int32_t out[4]) {

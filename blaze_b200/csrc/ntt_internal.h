@@ -46,6 +46,8 @@ struct NttPassParams {
   uint64_t otw_ra, otw_rb, otw_base, otw_scale;
   int store_k_fastest;              // store loop order (k fastest when a work item's outputs are contiguous)
   int scale_ninv;                   // multiply outputs by (2^log_root)^-1 (last pass of an inverse transform)
+  int* err;                         // first pass of a client transform: set to 1 when an input element is not canonical
+                                    // (>= r); null = no check
   NttTables tab;
 };
 

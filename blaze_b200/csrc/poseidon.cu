@@ -2,10 +2,10 @@
 //
 // Black box being replaced: the FPGA Poseidon core behind PoseidonClient
 // (/root/reference/src/ingo_hash/poseidon_api.rs:96-146): streaming hasher + 8-ary Merkle tree.
-// Parameter set (the reference's constants CSV is not in the repository -- parity UNPINNED):
-// width t = arity+1 in {9, 12}, R_F = 8, R_P = 57, Grain-LFSR round constants, Cauchy MDS,
-// state = [2^arity - 1, inputs...], output = state[1]; see oracle/py/poseidon.py for the same
-// definition in big integers.
+// Parameter set (the reference's constants CSV is not in the repository; the permutation itself is pinned by the
+// published Poseidon reference vector, tests/golden/external_kats.json): width t = arity+1 in {9, 12}, R_F = 8,
+// R_P = 57, Grain-LFSR round constants, Cauchy MDS (Filecoin neptune), state = [2^arity - 1, inputs...],
+// output = state[1]; see oracle/py/poseidon.py for the same definition in big integers.
 //
 // Layout: constants in global memory in Montgomery form (every thread of a warp reads the same
 // address: one broadcast transaction per load); the state lives in registers (t x 8 limbs).
@@ -41,73 +41,100 @@ __device__ __forceinline__ PE p_sbox(const PE& x) {
   return PF::mul(x4, x);
 }
 
-// canonical constants -> Montgomery; mds[i][j] = 1/(i + t + j)
-__global__ void k_poseidon_prepare(uint4* rc, int n_rc, uint4* mds, int t) {
+// canonical constants -> Montgomery form, in place
+__global__ void k_poseidon_prepare(uint4* consts, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n_rc) {
-    PE v = p_ld(rc + 2 * i);
-    p_st(rc + 2 * i, PF::to_mont(v));
-  } else if (i < n_rc + t * t) {
-    int k = i - n_rc;
-    int row = k / t, col = k % t;
-    PE v = PF::zero();
-    v.v[0] = (uint32_t)(row + t + col);
-    p_st(mds + 2 * k, PF::inv(PF::to_mont(v)));
-  }
+  if (i >= n) return;
+  PE v = p_ld(consts + 2 * i);
+  p_st(consts + 2 * i, PF::to_mont(v));
 }
 
-// in: n_hashes x arity canonical elements (32 B LE); out: n_hashes canonical digests
+// One thread per hash, state in registers, the OPTIMISED evaluation of the permutation (oracle/py/poseidon.py:
+// permute_optimized is the same computation in big integers): R_F dense rounds + one pre-sparse matrix, and R_P
+// partial rounds that add one constant, pass cell 0 through the S-box and multiply by a sparse matrix with 2t-1
+// non-trivial entries (t products for the new cell 0, one product-accumulate for each other cell) instead of t^2.
+// Constants: [half T] rc | [T T] mds | [T T] pre-sparse | R_P x (c0, row0[T], col0[T-1]) | [half T] rc, Montgomery form,
+// read with the same address by every lane (broadcast).
+//   raw = 0: in = n x (T-1) canonical elements; state = [2^(T-1) - 1, in...]; out = n canonical digests (cell 1)
+//   raw = 1: in / out = n x T canonical state cells (the bare permutation: known-answer tests)
+template <int T>
+__device__ __forceinline__ void p_dense(PE (&s)[T], const uint4* __restrict__ m) {
+  PE n[T];
+#pragma unroll
+  for (int i = 0; i < T; i++) {
+    PE acc = PF::mul(p_ld(m + 2 * (i * T)), s[0]);
+#pragma unroll
+    for (int j = 1; j < T; j++) acc = PF::add(acc, PF::mul(p_ld(m + 2 * (i * T + j)), s[j]));
+    n[i] = acc;
+  }
+#pragma unroll
+  for (int i = 0; i < T; i++) s[i] = n[i];
+}
+
 template <int T>
 __global__ void __launch_bounds__(128) k_poseidon_hash(const uint4* __restrict__ in, uint64_t n_hashes,
-                                                       const uint4* __restrict__ rc, const uint4* __restrict__ mds,
-                                                       int r_f, int r_p, uint4* __restrict__ out) {
+                                                       const uint4* __restrict__ consts, int r_f, int r_p, int raw,
+                                                       uint4* __restrict__ out) {
   uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (h >= n_hashes) return;
   constexpr int ARITY = T - 1;
+  const int half = r_f / 2;
+  const uint4* rc1 = consts;
+  const uint4* mds = rc1 + 2 * (half * T);
+  const uint4* pre = mds + 2 * (T * T);
+  const uint4* part = pre + 2 * (T * T);
+  const uint4* rc2 = part + 2 * ((size_t)r_p * 2 * T);
   PE s[T];
-  {
+  if (raw) {
+#pragma unroll
+    for (int i = 0; i < T; i++) s[i] = PF::to_mont(p_ld(in + 2 * (h * T + i)));
+  } else {
     PE tag = PF::zero();
     tag.v[0] = (1u << ARITY) - 1;
     s[0] = PF::to_mont(tag);
+#pragma unroll
+    for (int i = 0; i < ARITY; i++) s[i + 1] = PF::to_mont(p_ld(in + 2 * (h * ARITY + i)));
   }
+  for (int r = 0; r < half; r++) {
 #pragma unroll
-  for (int i = 0; i < ARITY; i++) s[i + 1] = PF::to_mont(p_ld(in + 2 * (h * ARITY + i)));
-  const int nr = r_f + r_p;
-  for (int r = 0; r < nr; r++) {
-#pragma unroll
-    for (int i = 0; i < T; i++) s[i] = PF::add(s[i], p_ld(rc + 2 * (r * T + i)));
-    bool full = r < r_f / 2 || r >= r_f / 2 + r_p;
-    s[0] = p_sbox(s[0]);
-    if (full) {
-#pragma unroll
-      for (int i = 1; i < T; i++) s[i] = p_sbox(s[i]);
-    }
-    PE n[T];
-#pragma unroll
-    for (int i = 0; i < T; i++) {
-      PE acc = PF::mul(p_ld(mds + 2 * (i * T)), s[0]);
-#pragma unroll
-      for (int j = 1; j < T; j++) acc = PF::add(acc, PF::mul(p_ld(mds + 2 * (i * T + j)), s[j]));
-      n[i] = acc;
-    }
-#pragma unroll
-    for (int i = 0; i < T; i++) s[i] = n[i];
+    for (int i = 0; i < T; i++) s[i] = p_sbox(PF::add(s[i], p_ld(rc1 + 2 * (r * T + i))));
+    p_dense<T>(s, r == half - 1 ? pre : mds);
   }
-  p_st(out + 2 * h, PF::from_mont(s[1]));
+  for (int r = 0; r < r_p; r++) {
+    const uint4* q = part + 2 * ((size_t)r * 2 * T);
+    const PE x0 = p_sbox(PF::add(s[0], p_ld(q)));
+    PE n0 = PF::mul(p_ld(q + 2), x0);
+#pragma unroll
+    for (int j = 1; j < T; j++) n0 = PF::add(n0, PF::mul(p_ld(q + 2 * (1 + j)), s[j]));
+#pragma unroll
+    for (int i = 1; i < T; i++) s[i] = PF::add(s[i], PF::mul(p_ld(q + 2 * (T + i)), x0));
+    s[0] = n0;
+  }
+  for (int r = 0; r < half; r++) {
+#pragma unroll
+    for (int i = 0; i < T; i++) s[i] = p_sbox(PF::add(s[i], p_ld(rc2 + 2 * (r * T + i))));
+    p_dense<T>(s, mds);
+  }
+  if (raw) {
+#pragma unroll
+    for (int i = 0; i < T; i++) p_st(out + 2 * (h * T + i), PF::from_mont(s[i]));
+  } else {
+    p_st(out + 2 * h, PF::from_mont(s[1]));
+  }
 }
 
-void poseidon_prepare(uint4* rc, int n_rc, uint4* mds, int t, cudaStream_t st) {
-  int n = n_rc + t * t;
-  k_poseidon_prepare<<<(n + 63) / 64, 64, 0, st>>>(rc, n_rc, mds, t);
+void poseidon_prepare(uint4* consts, int n, cudaStream_t st) {
+  k_poseidon_prepare<<<(n + 63) / 64, 64, 0, st>>>(consts, n);
   g_kernel_launches += 1;
 }
 
-void poseidon_hash(int t, const uint4* in, uint64_t n_hashes, const uint4* rc, const uint4* mds, int r_f, int r_p,
-                   uint4* out, cudaStream_t st) {
+void poseidon_hash(int t, const uint4* in, uint64_t n_hashes, const uint4* consts, int r_f, int r_p, int raw, uint4* out,
+                   cudaStream_t st) {
   if (!n_hashes) return;
   unsigned blocks = (unsigned)((n_hashes + 127) / 128);
-  if (t == 9) k_poseidon_hash<9><<<blocks, 128, 0, st>>>(in, n_hashes, rc, mds, r_f, r_p, out);
-  else k_poseidon_hash<12><<<blocks, 128, 0, st>>>(in, n_hashes, rc, mds, r_f, r_p, out);
+  if (t == 3) k_poseidon_hash<3><<<blocks, 128, 0, st>>>(in, n_hashes, consts, r_f, r_p, raw, out);
+  else if (t == 9) k_poseidon_hash<9><<<blocks, 128, 0, st>>>(in, n_hashes, consts, r_f, r_p, raw, out);
+  else k_poseidon_hash<12><<<blocks, 128, 0, st>>>(in, n_hashes, consts, r_f, r_p, raw, out);
   g_kernel_launches += 1;
 }
 

@@ -70,11 +70,227 @@ struct Grain {
       }
     }
   }
+  // one 255-bit draw, NOT rejection-sampled (the caller reduces it mod r): how the reference generator samples the MDS
+  void element_mod(uint8_t out[32]) {
+    memset(out, 0, 32);
+    for (int i = 0; i < 255; i++) {
+      int bitpos = 254 - i;
+      if (bit()) out[bitpos / 8] |= (uint8_t)(1u << (bitpos % 8));
+    }
+  }
 };
 
+// ---- host-side Fr(BLS12-381) for the one-off constant preprocessing (4 x 64-bit limbs, Montgomery, R = 2^256)
+namespace {
+typedef unsigned __int128 u128;
+struct Fr {
+  uint64_t v[4];
+};
+static const uint64_t FR_P[4] = {0xffffffff00000001ull, 0x53bda402fffe5bfeull, 0x3339d80809a1d805ull, 0x73eda753299d7d48ull};
+static const uint64_t FR_PINV = 0xfffffffeffffffffull;   // -p^-1 mod 2^64
+static bool fr_geq_p(const uint64_t* a) {
+  for (int i = 3; i >= 0; i--) { if (a[i] != FR_P[i]) return a[i] > FR_P[i]; }
+  return true;
+}
+static void fr_sub_p(uint64_t* a) {
+  u128 bo = 0;
+  for (int i = 0; i < 4; i++) { u128 t = (u128)a[i] - FR_P[i] - bo; a[i] = (uint64_t)t; bo = (t >> 64) & 1; }
+}
+static Fr fr_add(const Fr& a, const Fr& b) {
+  Fr r;
+  u128 c = 0;
+  for (int i = 0; i < 4; i++) { c += (u128)a.v[i] + b.v[i]; r.v[i] = (uint64_t)c; c >>= 64; }
+  if (c || fr_geq_p(r.v)) fr_sub_p(r.v);
+  return r;
+}
+static Fr fr_sub(const Fr& a, const Fr& b) {
+  Fr r;
+  u128 bo = 0;
+  for (int i = 0; i < 4; i++) { u128 t = (u128)a.v[i] - b.v[i] - bo; r.v[i] = (uint64_t)t; bo = (t >> 64) & 1; }
+  if (bo) { u128 c = 0; for (int i = 0; i < 4; i++) { c += (u128)r.v[i] + FR_P[i]; r.v[i] = (uint64_t)c; c >>= 64; } }
+  return r;
+}
+static Fr fr_mul(const Fr& a, const Fr& b) {   // a b / R mod p
+  uint64_t t[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < 4; i++) {
+    u128 c = 0;
+    for (int j = 0; j < 4; j++) { c += (u128)a.v[j] * b.v[i] + t[j]; t[j] = (uint64_t)c; c >>= 64; }
+    c += t[4]; t[4] = (uint64_t)c; t[5] = (uint64_t)(c >> 64);
+    const uint64_t m = t[0] * FR_PINV;
+    c = (u128)m * FR_P[0] + t[0];
+    c >>= 64;
+    for (int j = 1; j < 4; j++) { c += (u128)m * FR_P[j] + t[j]; t[j - 1] = (uint64_t)c; c >>= 64; }
+    c += t[4]; t[3] = (uint64_t)c; t[4] = t[5] + (uint64_t)(c >> 64);
+  }
+  Fr r;
+  memcpy(r.v, t, 32);
+  if (t[4] || fr_geq_p(r.v)) fr_sub_p(r.v);
+  return r;
+}
+static Fr fr_raw(uint64_t x) { Fr r = {{x, 0, 0, 0}}; return r; }
+static Fr FR_R2;   // R^2 mod p, computed once
+static void fr_init() {
+  static bool done = false;
+  if (done) return;
+  // R mod p by 256 doublings of 1, then R^2 = mont_mul-free: 256 more doublings of R
+  Fr x = fr_raw(1);
+  for (int i = 0; i < 512; i++) x = fr_add(x, x);
+  FR_R2 = x;
+  done = true;
+}
+static Fr fr_to_mont(const Fr& a) { return fr_mul(a, FR_R2); }
+static Fr fr_from_mont(const Fr& a) { return fr_mul(a, fr_raw(1)); }
+static Fr fr_from_u64(uint64_t x) { return fr_to_mont(fr_raw(x)); }
+static Fr fr_from_le(const uint8_t b[32]) { Fr r; memcpy(r.v, b, 32); while (fr_geq_p(r.v)) fr_sub_p(r.v); return fr_to_mont(r); }
+static void fr_to_le(const Fr& a, uint8_t out[32]) { Fr r = fr_from_mont(a); memcpy(out, r.v, 32); }
+static bool fr_is_zero(const Fr& a) { return !(a.v[0] | a.v[1] | a.v[2] | a.v[3]); }
+static Fr fr_inv(const Fr& a) {   // a^(p-2)
+  uint64_t e[4];
+  memcpy(e, FR_P, 32);
+  e[0] -= 2;
+  Fr r = fr_from_u64(1);
+  for (int i = 3; i >= 0; i--)
+    for (int b = 63; b >= 0; b--) {
+      r = fr_mul(r, r);
+      if ((e[i] >> b) & 1) r = fr_mul(r, a);
+    }
+  return r;
+}
+typedef std::vector<std::vector<Fr>> Mat;
+static Mat mat_mul(const Mat& a, const Mat& b) {
+  const size_t t = a.size();
+  Mat c(t, std::vector<Fr>(t, fr_raw(0)));
+  for (size_t i = 0; i < t; i++)
+    for (size_t j = 0; j < t; j++) {
+      Fr acc = fr_raw(0);
+      for (size_t k = 0; k < t; k++) acc = fr_add(acc, fr_mul(a[i][k], b[k][j]));
+      c[i][j] = acc;
+    }
+  return c;
+}
+static bool mat_inv(Mat a, Mat& out) {   // Gauss-Jordan
+  const size_t n = a.size();
+  out.assign(n, std::vector<Fr>(n, fr_raw(0)));
+  for (size_t i = 0; i < n; i++) out[i][i] = fr_from_u64(1);
+  for (size_t col = 0; col < n; col++) {
+    size_t piv = col;
+    while (piv < n && fr_is_zero(a[piv][col])) piv++;
+    if (piv == n) return false;
+    std::swap(a[col], a[piv]);
+    std::swap(out[col], out[piv]);
+    const Fr inv = fr_inv(a[col][col]);
+    for (size_t j = 0; j < n; j++) { a[col][j] = fr_mul(a[col][j], inv); out[col][j] = fr_mul(out[col][j], inv); }
+    for (size_t r = 0; r < n; r++) {
+      if (r == col || fr_is_zero(a[r][col])) continue;
+      const Fr f = a[r][col];
+      for (size_t j = 0; j < n; j++) {
+        a[r][j] = fr_sub(a[r][j], fr_mul(f, a[col][j]));
+        out[r][j] = fr_sub(out[r][j], fr_mul(f, out[col][j]));
+      }
+    }
+  }
+  return true;
+}
+}  // namespace
+
+// Constants of width t in the order the kernel reads them (canonical 32-byte LE; the device converts to Montgomery):
+//   [half t] first-half round constants | [t t] MDS | [t t] pre-sparse matrix | R_P x (c0, row0[t], col0[t-1]) |
+//   [half t] second-half round constants
+// The optimised form (constants pushed forward, sparse partial-round matrices) evaluates the SAME permutation as
+// round = add constants, S-box, MDS -- oracle/py/poseidon.py: optimized_params / permute_optimized is the big-integer
+// statement of this function and tests/test_poseidon_oracle.py checks the two against each other.
+static bool poseidon_constants(int t, int mds_mode, std::vector<uint8_t>& out) {
+  fr_init();
+  const int rp = P_RP, half = P_RF / 2, nr = P_RF + P_RP;
+  Grain g(255, t, P_RF, P_RP);
+  std::vector<std::vector<Fr>> c(nr, std::vector<Fr>(t));
+  for (int r = 0; r < nr; r++)
+    for (int i = 0; i < t; i++) { uint8_t le[32]; g.element(le); c[r][i] = fr_from_le(le); }
+  Mat mds(t, std::vector<Fr>(t));
+  if (mds_mode == 0) {   // Cauchy 1 / (i + t + j): Filecoin neptune's matrix
+    for (int i = 0; i < t; i++)
+      for (int j = 0; j < t; j++) mds[i][j] = fr_inv(fr_from_u64((uint64_t)(i + t + j)));
+  } else {               // x_i, y_j from the Grain stream behind the constants (Poseidon reference generator)
+    for (;;) {
+      std::vector<Fr> xy(2 * t);
+      for (auto& e : xy) { uint8_t le[32]; g.element_mod(le); e = fr_from_le(le); }
+      bool ok = true;
+      for (int i = 0; i < 2 * t && ok; i++)
+        for (int j = i + 1; j < 2 * t && ok; j++) ok = memcmp(xy[i].v, xy[j].v, 32) != 0;
+      for (int i = 0; i < t && ok; i++)
+        for (int j = 0; j < t && ok; j++) ok = !fr_is_zero(fr_add(xy[i], xy[t + j]));
+      if (!ok) continue;
+      for (int i = 0; i < t; i++)
+        for (int j = 0; j < t; j++) mds[i][j] = fr_inv(fr_add(xy[i], xy[t + j]));
+      break;
+    }
+  }
+  // constants of the partial rounds pushed forward through the MDS
+  std::vector<Fr> a(rp);
+  std::vector<Fr> k = c[half];
+  for (int r = 0; r < rp; r++) {
+    a[r] = k[0];
+    std::vector<Fr> nxt = c[half + r + 1];
+    for (int i = 0; i < t; i++)
+      for (int j = 1; j < t; j++) nxt[i] = fr_add(nxt[i], fr_mul(mds[i][j], k[j]));
+    k = nxt;
+  }
+  // sparse factorisation, last partial round first
+  std::vector<std::vector<Fr>> row0(rp), col0(rp);
+  Mat d = mds;
+  for (int it = 0; it < rp; it++) {
+    Mat dh(t - 1, std::vector<Fr>(t - 1)), dhi;
+    for (int i = 1; i < t; i++)
+      for (int j = 1; j < t; j++) dh[i - 1][j - 1] = d[i][j];
+    if (!mat_inv(dh, dhi)) return false;
+    const int r = rp - 1 - it;
+    row0[r].assign(t, fr_raw(0));
+    row0[r][0] = d[0][0];
+    for (int j = 0; j < t - 1; j++) {
+      Fr acc = fr_raw(0);
+      for (int q = 0; q < t - 1; q++) acc = fr_add(acc, fr_mul(d[0][1 + q], dhi[q][j]));
+      row0[r][1 + j] = acc;
+    }
+    col0[r].resize(t - 1);
+    for (int i = 1; i < t; i++) col0[r][i - 1] = d[i][0];
+    Mat p(t, std::vector<Fr>(t, fr_raw(0)));
+    p[0][0] = fr_from_u64(1);
+    for (int i = 1; i < t; i++)
+      for (int j = 1; j < t; j++) p[i][j] = dh[i - 1][j - 1];
+    d = mat_mul(p, mds);
+  }
+  out.clear();
+  auto put = [&](const Fr& x) { uint8_t le[32]; fr_to_le(x, le); out.insert(out.end(), le, le + 32); };
+  for (int r = 0; r < half; r++) for (int i = 0; i < t; i++) put(c[r][i]);
+  for (int i = 0; i < t; i++) for (int j = 0; j < t; j++) put(mds[i][j]);
+  for (int i = 0; i < t; i++) for (int j = 0; j < t; j++) put(d[i][j]);
+  for (int r = 0; r < rp; r++) {
+    put(a[r]);
+    for (int j = 0; j < t; j++) put(row0[r][j]);
+    for (int j = 0; j < t - 1; j++) put(col0[r][j]);
+  }
+  for (int i = 0; i < t; i++) put(k[i]);
+  for (int r = 1; r < half; r++) for (int i = 0; i < t; i++) put(c[half + rp + r][i]);
+  return true;
+}
+
+// host-only (no device needed): the optimised constants as canonical bytes, for the CPU test that compares them with
+// the oracle's big-integer derivation
+extern "C" int32_t bz_poseidon_optimized_constants(int32_t t, int32_t mds_mode, uint8_t* out, size_t out_cap, size_t* n_bytes) {
+  if (!n_bytes) return bz_fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null argument");
+  if ((t != 3 && t != 9 && t != 12) || (mds_mode != 0 && mds_mode != 1)) return bz_fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "width must be 3, 9 or 12; mds_mode 0 or 1");
+  std::vector<uint8_t> v;
+  if (!poseidon_constants(t, mds_mode, v)) return bz_fail(BZ_ERR_UNKNOWN, "singular sub-matrix while factoring the MDS");
+  *n_bytes = v.size();
+  if (out) {
+    if (out_cap < v.size()) return bz_fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "buffer too small (%zu < %zu)", out_cap, v.size());
+    memcpy(out, v.data(), v.size());
+  }
+  return BZ_OK;
+}
+
 struct PoseidonParams {
-  uint4* rc = nullptr;    // (RF+RP)*t elements, Montgomery
-  uint4* mds = nullptr;   // t*t
+  uint4* consts = nullptr;   // Montgomery form, layout of poseidon_constants()
   bool ready = false;
 };
 
@@ -84,7 +300,7 @@ struct bz_poseidon {
   uint32_t height = 0;
   int tree_mode = 0;
   int in_arity = 11;
-  PoseidonParams par[2];   // [0]: t = 9 (arity 8), [1]: t = 12 (arity 11)
+  PoseidonParams par[3][2];   // [width index: 0 -> t = 3, 1 -> t = 9, 2 -> t = 12][mds mode]
   // element stream
   std::vector<uint8_t> staged;      // host staging of elements not yet on the device (32 B each)
   uint64_t elems_total = 0;         // elements received since initialize (ring id = elems_total - 1)
@@ -94,23 +310,25 @@ struct bz_poseidon {
   uint64_t d_inputs_cap = 0;
   std::vector<uint8_t*> d_layer;    // node digests per layer
   std::vector<uint64_t> layer_size, done;
-  std::deque<std::vector<uint8_t>> pending;   // 64-byte records
+  std::vector<uint8_t> pending;     // 64-byte records, FIFO: [pending_head, pending.size() / 64)
+  size_t pending_head = 0;
   uint32_t last_hash_id = 0;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  double device_ms = 0;             // kernel time since initialize (CUDA events around every hash launch)
   std::mutex mu;
 };
 
-static int32_t ensure_params(bz_poseidon* p, int t) {
-  PoseidonParams& q = p->par[t == 9 ? 0 : 1];
+static int width_index(int t) { return t == 3 ? 0 : (t == 9 ? 1 : 2); }
+
+static int32_t ensure_params(bz_poseidon* p, int t, int mds_mode = 0) {
+  PoseidonParams& q = p->par[width_index(t)][mds_mode];
   if (q.ready) return BZ_OK;
-  int n_rc = (P_RF + P_RP) * t;
-  std::vector<uint8_t> host((size_t)n_rc * 32);
-  Grain g(255, t, P_RF, P_RP);
-  for (int i = 0; i < n_rc; i++) g.element(&host[(size_t)i * 32]);
-  CUDA_TRY(BZ_ERR_WRITE, cudaMalloc((void**)&q.rc, (size_t)n_rc * 32));
-  CUDA_TRY(BZ_ERR_WRITE, cudaMalloc((void**)&q.mds, (size_t)t * t * 32));
+  std::vector<uint8_t> host;
+  if (!poseidon_constants(t, mds_mode, host)) return bz_fail(BZ_ERR_UNKNOWN, "singular sub-matrix while factoring the MDS");
+  CUDA_TRY(BZ_ERR_WRITE, cudaMalloc((void**)&q.consts, host.size()));
   cudaStream_t st = dc_stream(p->dc);
-  CUDA_TRY(BZ_ERR_WRITE, cudaMemcpyAsync(q.rc, host.data(), host.size(), cudaMemcpyHostToDevice, st));
-  poseidon_prepare(q.rc, n_rc, q.mds, t, st);
+  CUDA_TRY(BZ_ERR_WRITE, cudaMemcpyAsync(q.consts, host.data(), host.size(), cudaMemcpyHostToDevice, st));
+  poseidon_prepare(q.consts, (int)(host.size() / 32), st);
   CUDA_TRY(BZ_ERR_UNKNOWN, cudaStreamSynchronize(st));
   q.ready = true;
   return BZ_OK;
@@ -124,6 +342,8 @@ extern "C" int32_t bz_poseidon_new(bz_dclient* dc, int32_t hash_type, bz_poseido
   if (hash_type != 0) return bz_fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "unknown hash type %d", hash_type);
   bz_poseidon* p = new bz_poseidon();
   p->dc = dc;
+  cudaEventCreate(&p->ev[0]);
+  cudaEventCreate(&p->ev[1]);
   *out = p;
   return BZ_OK;
 }
@@ -141,7 +361,8 @@ extern "C" int32_t bz_poseidon_free(bz_poseidon* p) {
   cudaSetDevice(dc_device(p->dc));
   cudaStreamSynchronize(dc_stream(p->dc));
   free_tree(p);
-  for (auto& q : p->par) { if (q.rc) cudaFree(q.rc); if (q.mds) cudaFree(q.mds); }
+  for (auto& w : p->par) for (auto& q : w) if (q.consts) cudaFree(q.consts);
+  for (auto& e : p->ev) if (e) cudaEventDestroy(e);
   delete p;
   return BZ_OK;
 }
@@ -185,6 +406,8 @@ extern "C" int32_t bz_poseidon_initialize(bz_poseidon* p, uint32_t tree_height, 
   CUDA_TRY(BZ_ERR_WRITE, cudaMalloc((void**)&p->d_inputs, p->d_inputs_cap * 32));
   p->staged.clear();
   p->pending.clear();
+  p->pending_head = 0;
+  p->device_ms = 0;
   p->elems_total = p->elems_tree = p->elems_on_device = 0;
   p->last_hash_id = 0;
   p->initialized = true;
@@ -207,21 +430,29 @@ static int32_t flush(bz_poseidon* p) {
     if (avail <= p->done[l]) break;
     uint64_t n = avail - p->done[l];
     int t = (l == 0 && p->in_arity == 11) ? 12 : 9;
-    const PoseidonParams& q = p->par[t == 9 ? 0 : 1];
+    const PoseidonParams& q = p->par[width_index(t)][0];
     const uint8_t* in = l == 0 ? p->d_inputs + p->done[0] * (uint64_t)p->in_arity * 32 : p->d_layer[l - 1] + p->done[l] * 8 * 32;
     uint8_t* out = p->d_layer[l] + p->done[l] * 32;
-    poseidon_hash(t, (const uint4*)in, n, q.rc, q.mds, P_RF, P_RP, (uint4*)out, st);
+    cudaEventRecord(p->ev[0], st);
+    poseidon_hash(t, (const uint4*)in, n, q.consts, P_RF, P_RP, 0, (uint4*)out, st);
+    cudaEventRecord(p->ev[1], st);
     CUDA_TRY(BZ_ERR_UNKNOWN, cudaGetLastError());
     host.resize(n * 32);
     CUDA_TRY(BZ_ERR_READ, cudaMemcpyAsync(host.data(), out, n * 32, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(BZ_ERR_READ, cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, p->ev[0], p->ev[1]);
+    p->device_ms += ms;
+    if (p->pending_head && p->pending_head * 64 == p->pending.size()) { p->pending.clear(); p->pending_head = 0; }
+    const size_t at = p->pending.size();
+    p->pending.resize(at + n * 64);
     for (uint64_t i = 0; i < n; i++) {
-      std::vector<uint8_t> rec(64, 0);
-      memcpy(rec.data(), &host[i * 32], 32);
+      uint8_t* rec = &p->pending[at + i * 64];
+      memcpy(rec, &host[i * 32], 32);
+      memset(rec + 32, 0, 32);
       uint64_t id = p->done[l] + i;
       uint64_t meta = (id & 0x3fffffffull) | ((uint64_t)l << 30);   // poseidon_api.rs:50-61
-      memcpy(rec.data() + 32, &meta, 8);
-      p->pending.push_back(std::move(rec));
+      memcpy(rec + 32, &meta, 8);
     }
     p->done[l] = avail;
   }
@@ -244,18 +475,28 @@ extern "C" int32_t bz_poseidon_set_data(bz_poseidon* p, const uint8_t* input, si
   // u32::to_le_bytes(), integration_poseidon.rs:49-51,109-116); longer: a whole number of 32-byte elements
   size_t n_el = len <= 32 ? 1 : len / 32;
   if (len > 32 && len % 32) return bz_fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "bulk set_data length must be a multiple of 32");
-  for (size_t e = 0; e < n_el; e++) {
+  size_t e = 0;
+  while (e < n_el) {
     if (p->elems_tree == p->d_inputs_cap) {   // previous tree's inputs are full: finish it first
       rc = flush(p);
       if (rc) return rc;
       if (p->elems_tree == p->d_inputs_cap) return bz_fail(BZ_ERR_WRITE, "input ring full");
     }
-    uint8_t el[32];
-    memset(el, 0, 32);
-    memcpy(el, input + e * 32, len <= 32 ? len : 32);
-    p->staged.insert(p->staged.end(), el, el + 32);
-    p->elems_total++;
-    p->elems_tree++;
+    if (len <= 32) {
+      uint8_t el[32];
+      memset(el, 0, 32);
+      memcpy(el, input, len);
+      p->staged.insert(p->staged.end(), el, el + 32);
+      e = 1;
+      p->elems_total++;
+      p->elems_tree++;
+    } else {   // bulk: as many whole elements as the current tree still takes
+      const size_t take = (size_t)std::min<uint64_t>(n_el - e, p->d_inputs_cap - p->elems_tree);
+      p->staged.insert(p->staged.end(), input + e * 32, input + (e + take) * 32);
+      e += take;
+      p->elems_total += take;
+      p->elems_tree += take;
+    }
   }
   return BZ_OK;
 }
@@ -267,21 +508,22 @@ extern "C" int32_t bz_poseidon_get_num_of_pending_results(bz_poseidon* p, uint32
   std::lock_guard<std::mutex> lk(p->mu);
   rc = flush(p);
   if (rc) return rc;
-  *n = (uint32_t)p->pending.size();
+  *n = (uint32_t)(p->pending.size() / 64 - p->pending_head);
   return BZ_OK;
 }
 
 extern "C" int32_t bz_poseidon_get_raw_results(bz_poseidon* p, uint32_t num_of_results, uint8_t* out) {
   if (!p || (!out && num_of_results)) return bz_fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null argument");
   std::lock_guard<std::mutex> lk(p->mu);
-  if (num_of_results > p->pending.size()) return bz_fail(BZ_ERR_READ, "only %zu results pending", p->pending.size());
-  for (uint32_t i = 0; i < num_of_results; i++) {
-    const std::vector<uint8_t>& rec = p->pending.front();
-    memcpy(out + (size_t)i * 64, rec.data(), 64);
+  const size_t have = p->pending.size() / 64 - p->pending_head;
+  if (num_of_results > have) return bz_fail(BZ_ERR_READ, "only %zu results pending", have);
+  if (num_of_results) {
+    const uint8_t* src = &p->pending[p->pending_head * 64];
+    memcpy(out, src, (size_t)num_of_results * 64);
     uint32_t id;
-    memcpy(&id, rec.data() + 32, 4);
+    memcpy(&id, src + (size_t)(num_of_results - 1) * 64 + 32, 4);
     p->last_hash_id = id & 0x3fffffffu;
-    p->pending.pop_front();
+    p->pending_head += num_of_results;
   }
   return BZ_OK;
 }
@@ -327,3 +569,36 @@ extern "C" int32_t bz_poseidon_start_process(bz_poseidon* p) {
   return flush(p);
 }
 extern "C" int32_t bz_poseidon_wait_result(bz_poseidon* p) { return bz_poseidon_start_process(p); }
+
+// ---- B200 additions
+// kernel milliseconds since initialize() (CUDA events around every hash launch): the device-side cost of the tree
+extern "C" int32_t bz_poseidon_device_ms(bz_poseidon* p, float* ms) {
+  if (!p || !ms) return bz_fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null argument");
+  std::lock_guard<std::mutex> lk(p->mu);
+  *ms = (float)p->device_ms;
+  return BZ_OK;
+}
+
+// n raw permutations of width t (3, 9 or 12) on full states (n x t canonical elements in and out), with the Cauchy
+// (mds_mode 0: the PoseidonClient instances) or the Grain-sampled MDS (1: the parameter set of the published
+// Poseidon reference vectors): lets tests run known-answer vectors and random states through the CUDA kernel
+extern "C" int32_t bz_poseidon_permute(bz_poseidon* p, int32_t t, int32_t mds_mode, const uint8_t* in, size_t n, uint8_t* out) {
+  if (!p || !in || !out || !n) return bz_fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "bad argument");
+  if ((t != 3 && t != 9 && t != 12) || (mds_mode != 0 && mds_mode != 1)) return bz_fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "width must be 3, 9 or 12; mds_mode 0 or 1");
+  int32_t rc = dc_select(p->dc);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(p->mu);
+  rc = ensure_params(p, t, mds_mode);
+  if (rc) return rc;
+  const size_t bytes = n * (size_t)t * 32;
+  uint8_t* d = nullptr;
+  CUDA_TRY(BZ_ERR_WRITE, cudaMalloc((void**)&d, 2 * bytes));
+  cudaStream_t st = dc_stream(p->dc);
+  cudaMemcpyAsync(d, in, bytes, cudaMemcpyHostToDevice, st);
+  poseidon_hash(t, (const uint4*)d, n, p->par[width_index(t)][mds_mode].consts, P_RF, P_RP, 1, (uint4*)(d + bytes), st);
+  cudaMemcpyAsync(out, d + bytes, bytes, cudaMemcpyDeviceToHost, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(d);
+  if (e != cudaSuccess) return bz_fail(BZ_ERR_UNKNOWN, "permutation failed: %s", cudaGetErrorString(e));
+  return BZ_OK;
+}

@@ -34,7 +34,8 @@ class DMA_RW(enum.IntEnum):        # dclient_code.rs:67-69
 
 
 class DriverClient:
-    """dclient.rs:50-86.  `id` is the slot string of the reference = CUDA device ordinal."""
+    """dclient.rs:50-86.  `id` is the slot string of the reference = CUDA device ordinal; a comma-separated list
+    ("0,1,2,3") opens one client over several devices (MSMClient then shards over them)."""
 
     def __init__(self, id="0", cfg=None):
         self.cfg = cfg or DriverConfig()
@@ -95,6 +96,31 @@ class DriverClient:
         p, n, keep = buf_ptr(binary)
         check(lib().bz_dclient_load_binary(self._h, p, n))
         return 0
+
+    # -- multi-GPU (B200 additions; see include/blaze_b200.h)
+    def device_count(self):
+        """Devices behind this client: 1, or the length of an id list such as "0,1,2,3"."""
+        n = ctypes.c_uint32()
+        check(lib().bz_dclient_device_count(self._h, ctypes.byref(n)))
+        return n.value
+
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """128-byte NCCL id: make it on one rank, hand it to every rank, pass it to comm_init."""
+        out = ctypes.create_string_buffer(128)
+        check(lib().bz_comm_unique_id(out))
+        return out.raw
+
+    def comm_init(self, rank: int, world: int, unique_id: bytes):
+        """One process per GPU: this client becomes rank `rank` of `world`; MSM results are summed over the ranks
+        device-side (NCCL all-gather + combine kernel on the client's stream)."""
+        assert len(unique_id) == 128
+        check(lib().bz_dclient_comm_init(self._h, int(rank), int(world), unique_id))
+
+    def comm_info(self):
+        r, w = ctypes.c_int32(), ctypes.c_int32()
+        check(lib().bz_dclient_comm_info(self._h, ctypes.byref(r), ctypes.byref(w)))
+        return r.value, w.value
 
     def device_info(self):
         name = ctypes.create_string_buffer(128)

@@ -128,5 +128,21 @@ class PoseidonClient(DriverPrimitive):
         check(lib().bz_poseidon_get_last_hash_sent_to_host(self._h, ctypes.byref(v)))
         return v.value
 
+    # ---- B200 additions
+    def device_ms(self):
+        """Kernel milliseconds since initialize() (the analogue of the core's clock counters)."""
+        v = ctypes.c_float()
+        check(lib().bz_poseidon_device_ms(self._h, ctypes.byref(v)))
+        return v.value
+
+    def permute(self, states: bytes, t: int, mds_mode: int = 0) -> bytes:
+        """Bare permutation of len(states) / (32 t) states of width t (3, 9, 12); mds_mode 1 = Grain-sampled MDS."""
+        n = len(states) // (32 * t)
+        out = bytearray(n * t * 32)
+        ip, _, k1 = buf_ptr(states)
+        op, _, k2 = buf_ptr(out)
+        check(lib().bz_poseidon_permute(self._h, t, mds_mode, ip, n, op))
+        return bytes(out)
+
     def log_api_values(self):                                 # poseidon_api.rs:245-253
         return {"last_element": self.get_last_element_sent_to_ring(), "last_hash": self.get_last_hash_sent_to_host()}

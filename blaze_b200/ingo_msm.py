@@ -143,8 +143,28 @@ class MSMClient(DriverPrimitive):
         check(lib().bz_msm_get_data_from_hbm(self._h, p, n, int(addr), int(offset)))
         return bytes(out)
 
-    def get_api(self):                                        # msm_api.rs:324-330 (counter dump)
-        return {"phase_ms": self.phase_times(), "plan": self.plan_info(), "label": self.task_label()}
+    def get_api(self):                                        # msm_api.rs:324-330: read every INGO_MSM_ADDR register
+        """{register name: value} for every offset of msm_hw_code.rs:6-55 (the RESULT window 0x38..0xc4 is returned
+        as bytes).  The reference reads and discards them; log_api_values() prints them."""
+        regs = (ctypes.c_uint32 * 82)()
+        check(lib().bz_msm_get_api(self._h, regs, 82))
+        out = {}
+        for name, off in INGO_MSM_ADDR.items():
+            if name == "ADDR_HIF2CPU_C_RESULT":
+                out[name] = bytes(bytearray(regs)[off:off + self.result_point_size])
+            else:
+                out[name] = regs[off // 4]
+        return out
+
+    def log_api_values(self):
+        import logging
+        for k, v in self.get_api().items():
+            logging.getLogger("ingo_blaze").debug("%s: %s", k, v.hex() if isinstance(v, bytes) else hex(v))
+
+    def table_build_ms(self):
+        v = ctypes.c_float()
+        check(lib().bz_msm_table_build_ms(self._h, ctypes.byref(v)))
+        return v.value
 
     # ---- B200 additions
     def phase_times(self):
@@ -185,6 +205,10 @@ class MSMClient(DriverPrimitive):
         p, ln, keep = buf_ptr(p0q)
         check(lib().bz_msm_generate_chain_points(self._h, p, ln, int(first), int(n), int(addr), int(offset)))
 
+    def expand_precompute(self, src_addr: int, n: int, dst_addr: int):
+        """n factor-1 bases at src_addr -> the reference's x8 records (P, 2^32 P, ..) at dst_addr, on the device."""
+        check(lib().bz_msm_expand_precompute(self._h, int(src_addr), int(n), int(dst_addr)))
+
     def field_selftest(self, a: bytes, b: bytes, n: int, op: int) -> bytes:
         out = bytearray(len(a))
         ap, _, k1 = buf_ptr(a)
@@ -192,6 +216,35 @@ class MSMClient(DriverPrimitive):
         op_, _, k3 = buf_ptr(out)
         check(lib().bz_msm_field_selftest(self._h, ap, bp, op_, n, op))
         return bytes(out)
+
+
+# msm_hw_code.rs:6-55
+INGO_MSM_ADDR = {
+    "ADDR_HIF2CPU_C_IMAGE_ID": 0x0, "ADDR_HIF2CPU_C_IMAGE_PARAMTERS": 0x4, "ADDR_HIF2CPU_C_MSM_ENGINE_READY": 0x8,
+    "ADDR_HIF2CPU_C_MSM_TASK_LABEL": 0xc, "ADDR_CPU2HIF_C_BASES_HBM_START_ADDRESS_LO": 0x10,
+    "ADDR_CPU2HIF_C_BASES_HBM_START_ADDRESS_HI": 0x14, "ADDR_CPU2HIF_C_BASES_SOURCE": 0x18,
+    "ADDR_CPU2HIF_C_COEFFICIENTS_HBM_START_ADDRESS_LO": 0x1c, "ADDR_CPU2HIF_C_COEFFICIENTS_HBM_START_ADDRESS_HI": 0x20,
+    "ADDR_CPU2HIF_C_COEFFICIENTS_SOURCE": 0x24, "ADDR_CPU2HIF_C_NUMBER_OF_MSM_ELEMENTS": 0x28,
+    "ADDR_CPU2HIF_E_PUSH_MSM_TASK_TO_QUEUE": 0x2c, "ADDR_HIF2CPU_C_RESULT_VALID": 0x30, "ADDR_HIF2CPU_C_RESULT_LABEL": 0x34,
+    "ADDR_HIF2CPU_C_RESULT": 0x38, "ADDR_CPU2HIF_E_POP_RESULT": 0xc8, "ADDR_HIF2CPU_C_NOF_PENDING_TASKS_IN_QUEUE": 0xcc,
+    "ADDR_HIF2CPU_C_NOF_PENDING_RESULTS_IN_QUEUE": 0xd0, "ADDR_CPU2HIF_C_OPTIMIZATIONS": 0xd4,
+    "ADDR_HIF2CPU_C_TASK_IN_FINAL_ACCUMULATION_PHASE": 0xd8, "ADDR_HIF2CPU_C_NOF_ELEMENTS_LEFT_IN_CURRENT_TASK": 0xdc,
+    "ADDR_AXI2CPU_C_NUMBER_OF_COEFFICIENTS_IN_AXI_DMA_FIFO": 0xe0, "ADDR_AXI2CPU_C_NUMBER_OF_BASES_IN_AXI_DMA_FIFO": 0xe4,
+    "ADDR_AXI2CPU_C_NUMBER_OF_COEFFICIENTS_IN_AXI_HBM_FIFO": 0xe8, "ADDR_AXI2CPU_C_NUMBER_OF_BASES_IN_AXI_HBM_FIFO": 0xec,
+    "ADDR_HIF2CPU_E_BUCKET_ACCUMULATION_PHASE_COMPLETED": 0xf0, "ADDR_HIF2CPU_E_FINAL_ACCUMULATION_PHASE_COMPLETED": 0xf4,
+    "ADDR_HIF2CPU_C_LAST_TASK_PHASE1_TOTAL_CLOCKS_LO": 0xf8, "ADDR_HIF2CPU_C_LAST_TASK_PHASE1_TOTAL_CLOCKS_HI": 0xfc,
+    "ADDR_HIF2CPU_C_LAST_TASK_PHASE1_BUSY_ECADDER_CLOCKS_LO": 0x100, "ADDR_HIF2CPU_C_LAST_TASK_PHASE1_BUSY_ECADDER_CLOCKS_HI": 0x104,
+    "ADDR_HIF2CPU_C_LAST_TASK_PHASE2_TOTAL_CLOCKS_LO": 0x108, "ADDR_HIF2CPU_C_LAST_TASK_PHASE2_TOTAL_CLOCKS_HI": 0x10c,
+    "ADDR_HIF2CPU_C_LAST_TASK_PHASE2_BUSY_ECADDER_CLOCKS_LO": 0x110, "ADDR_HIF2CPU_C_LAST_TASK_PHASE2_BUSY_ECADDER_CLOCKS_HI": 0x114,
+    "ADDR_HIF2CPU_C_LAST_TASK_PHASE3_TOTAL_CLOCKS_LO": 0x118, "ADDR_HIF2CPU_C_LAST_TASK_PHASE3_TOTAL_CLOCKS_HI": 0x11c,
+    "ADDR_HIF2CPU_C_LAST_TASK_PHASE3_BUSY_ECADDER_CLOCKS_LO": 0x120, "ADDR_HIF2CPU_C_LAST_TASK_PHASE3_BUSY_ECADDER_CLOCKS_HI": 0x124,
+    "ADDR_HIF2CPU_C_LAST_TASK_PHASE1_COEFFICIENTS_FIFO_BUSY_CLOCKS_LO": 0x128,
+    "ADDR_HIF2CPU_C_LAST_TASK_PHASE1_COEFFICIENTS_FIFO_BUSY_CLOCKS_HI": 0x12c,
+    "ADDR_HIF2CPU_C_LAST_TASK_PHASE1_COEFFICIENTS_FIFO_NOF_EMPTY_LO": 0x130,
+    "ADDR_HIF2CPU_C_LAST_TASK_PHASE1_COEFFICIENTS_FIFO_NOF_EMPTY_HI": 0x134,
+    "ADDR_HIF2CPU_C_LAST_TASK_PHASE1_BASES_FIFO_BUSY_CLOCKS_LO": 0x138, "ADDR_HIF2CPU_C_LAST_TASK_PHASE1_BASES_FIFO_BUSY_CLOCKS_HI": 0x13c,
+    "ADDR_HIF2CPU_C_LAST_TASK_PHASE1_BASES_FIFO_NOF_EMPTY_LO": 0x140, "ADDR_HIF2CPU_C_LAST_TASK_PHASE1_BASES_FIFO_NOF_EMPTY_HI": 0x144,
+}
 
 
 class MSMImageParametrs:       # msm_api.rs:333-364 (sic: the reference's spelling)

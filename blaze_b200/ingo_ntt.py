@@ -122,7 +122,9 @@ class DistributedNTT:
         check(lib().bz_ntt_dist_new(dclient._h, int(field), int(log_size), 1 if inverse else 0, rank, world,
                                     ctypes.byref(h)))
         self._h = h
-        if world > 1:
+        # a ranked DriverClient (comm_init) exchanges the handles itself and supplies device-side barriers
+        self._comm = world > 1 and dclient.comm_info() == (rank, world)
+        if world > 1 and not self._comm:
             mine = ctypes.create_string_buffer(64)
             check(lib().bz_ntt_dist_ipc_handle(self._h, mine))
             handles = exchange(mine.raw)
@@ -155,6 +157,10 @@ class DistributedNTT:
 
     def run(self):
         """step1 (columns + twiddle + peer stores) -> barrier -> step3 (rows)."""
+        if self._comm or self.world == 1:
+            check(lib().bz_ntt_dist_run(self._h))      # stream-ordered, barriers on the device
+            check(lib().bz_ntt_dist_sync(self._h))
+            return
         self._barrier()                 # every rank's exchange buffer is free again
         check(lib().bz_ntt_dist_step1(self._h))
         check(lib().bz_ntt_dist_sync(self._h))

@@ -64,8 +64,22 @@ const char* bz_version(void);
 uint64_t bz_kernel_launch_count(void);
 
 /* ------------------------------------------------------------------ DriverClient
- * `id` is the reference's FPGA slot string (dclient.rs:79-86, env ID) = CUDA device ordinal. */
+ * `id` is the reference's FPGA slot string (dclient.rs:79-86, env ID) = CUDA device ordinal.  A comma-separated list
+ * ("0,1,2,3,4,5,6,7") opens ONE client over several devices: an MSMClient created on it shards its bases and scalars
+ * over the devices and returns one result per task (the final sum runs device-side over NVLink); NTTClient,
+ * PoseidonClient and dma_write / dma_read use the first device of the list. */
 int32_t bz_dclient_new(const char* id, int32_t card_type, bz_dclient** out);          /* dclient.rs:79-86   */
+/* number of devices behind the handle (1 for a plain id) */
+int32_t bz_dclient_device_count(bz_dclient* dc, uint32_t* n);
+/* One process per GPU (torchrun / MPI style): turn a single-device client into rank `rank` of `world` processes.
+ * `unique_id` is the 128-byte NCCL id made by bz_comm_unique_id() on one rank and handed to all of them by the caller.
+ * An MSMClient on such a client treats its inputs as THIS rank's shard of a point-sharded MSM; the ranks' partial
+ * results are all-gathered with NCCL and summed on the client's stream, so result() returns the same full sum on every
+ * rank.  All ranks must issue the same sequence of tasks.  bz_ntt_dist_* uses the communicator for its handle exchange
+ * and its barrier. */
+int32_t bz_comm_unique_id(uint8_t out[128]);
+int32_t bz_dclient_comm_init(bz_dclient* dc, int32_t rank, int32_t world, const uint8_t unique_id[128]);
+int32_t bz_dclient_comm_info(bz_dclient* dc, int32_t* rank, int32_t* world);
 int32_t bz_dclient_free(bz_dclient* dc);
 int32_t bz_dclient_reset(bz_dclient* dc);                                              /* dclient.rs:88-93   */
 /* flat card address space (dclient.rs:456-517): bytes land in / come from the device arena */
@@ -118,6 +132,13 @@ int32_t bz_msm_sizes(bz_msm* m, uint32_t* scalar_size, uint32_t* point_size, uin
 int32_t bz_msm_phase_times(bz_msm* m, float ms[4]);
 /* override the window size chosen by the cost model (0 = automatic) */
 int32_t bz_msm_set_window_bits(bz_msm* m, int32_t c);
+/* get_api() (msm_api.rs:324-330): the register file of the MSM core, indexed by INGO_MSM_ADDR offset / 4
+ * (msm_hw_code.rs:6-55; 82 words, 0x000..0x144).  Task / result queue registers reflect the client's queues; the
+ * LAST_TASK_PHASE* clock counters are the CUDA-event times of the last completed task in SM clocks (phase 1 = ingest,
+ * sort and bucket accumulation, "busy EC adder" = the accumulation kernel alone; phase 2 = final accumulation). */
+int32_t bz_msm_get_api(bz_msm* m, uint32_t* regs, size_t n_words);
+/* milliseconds the last build of the window-merged table took (0 if none was built) */
+int32_t bz_msm_table_build_ms(bz_msm* m, float* ms);
 /* plan of the last launched task: c, W, buckets/window, segment length */
 int32_t bz_msm_plan_info(bz_msm* m, uint32_t out[4]);
 /* extended plan: c, digit windows (mixed adds per scalar), buckets/set, segment length, bucket sets,
@@ -143,6 +164,9 @@ int32_t bz_msm_combine_results(bz_msm* m, const uint8_t* records, int32_t n, uin
  * into the card address space at addr+offset; p0q = P0 || Q in wire format */
 int32_t bz_msm_generate_chain_points(bz_msm* m, const uint8_t* p0q, size_t p0q_len, uint64_t first, uint64_t n,
                                      uint64_t addr, uint64_t offset);
+/* derive the reference's x8 precomputed records (P, 2^32 P, .., 2^224 P per base; tests/msm/mod.rs:360-380) on the device:
+ * n factor-1 bases at src_addr -> n x 8 wire points at dst_addr of the card address space */
+int32_t bz_msm_expand_precompute(bz_msm* m, uint64_t src_addr, uint64_t n, uint64_t dst_addr);
 /* device self-test of the base-field arithmetic: out[i] = a[i] (op) b[i], canonical LE elements;
  * op: 0 mul, 1 add, 2 sub, 3 sqr, 4 inv, 5 neg */
 int32_t bz_msm_field_selftest(bz_msm* m, const uint8_t* a, const uint8_t* b, uint8_t* out, int32_t n, int32_t op);
@@ -187,6 +211,9 @@ int32_t bz_ntt_dist_buffers(bz_ntt_dist* t, uint64_t* slab_in_dev, uint64_t* blo
 int32_t bz_ntt_dist_step1(bz_ntt_dist* t);
 int32_t bz_ntt_dist_sync(bz_ntt_dist* t);   /* drains the rank's stream; the cross-rank barrier is the caller's */
 int32_t bz_ntt_dist_step3(bz_ntt_dist* t);
+/* whole transform on the client's stream with device-side (NCCL) barriers; needs a ranked DriverClient
+ * (bz_dclient_comm_init), which also exchanges the IPC handles inside bz_ntt_dist_new */
+int32_t bz_ntt_dist_run(bz_ntt_dist* t);
 int32_t bz_ntt_dist_times(bz_ntt_dist* t, float ms[2]);   /* CUDA-event ms of the last step1 / step3 */
 int32_t bz_ntt_dist_plan(bz_ntt_dist* t, int32_t out[4]);   /* log2 N1, log2 N2, column passes, row passes */
 
@@ -214,6 +241,15 @@ int32_t bz_poseidon_get_last_element_sent_to_ring(bz_poseidon* p, uint32_t* id);
 int32_t bz_poseidon_get_num_of_pending_results(bz_poseidon* p, uint32_t* n);            /* :156-161 */
 int32_t bz_poseidon_get_raw_results(bz_poseidon* p, uint32_t num_of_results, uint8_t* out); /* :191-196 */
 int32_t bz_poseidon_get_last_hash_sent_to_host(bz_poseidon* p, uint32_t* id);           /* :198-203 */
+/* --- B200 additions --- */
+/* kernel milliseconds spent since initialize() (the analogue of the core's clock counters, hash_hw_code.rs:16-24) */
+int32_t bz_poseidon_device_ms(bz_poseidon* p, float* ms);
+/* n bare permutations of width t (3, 9 or 12) over full states of canonical elements; mds_mode 0 = the Cauchy matrix
+ * the client uses, 1 = the Grain-sampled matrix of the published Poseidon reference vectors (known-answer tests) */
+int32_t bz_poseidon_permute(bz_poseidon* p, int32_t t, int32_t mds_mode, const uint8_t* in, size_t n, uint8_t* out);
+/* host-only: the preprocessed constants of width t (canonical bytes, kernel order: first-half round constants, MDS,
+ * pre-sparse matrix, R_P x (c0, row0[t], col0[t-1]), second-half round constants); out may be NULL to query the size */
+int32_t bz_poseidon_optimized_constants(int32_t t, int32_t mds_mode, uint8_t* out, size_t out_cap, size_t* n_bytes);
 
 #ifdef __cplusplus
 }

@@ -145,3 +145,91 @@ def parse_record(rec):
     hash_id = int.from_bytes(meta[0:4], "little") & 0x3fffffff
     layer_id = int.from_bytes(meta[3:5] + b"\0\0", "little") >> 6
     return h, hash_id, layer_id
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Optimised evaluation of the SAME permutation (Poseidon paper, appendix on efficient implementation; what Filecoin's
+# neptune calls "static optimised" hashing).  The product's CUDA kernel evaluates this form; tests check that it
+# equals permute() above on every input, so it changes cost, not values.
+#   * constants: in a partial round only cell 0 passes the S-box, so the constants of the other cells commute with it
+#     and are pushed forward through the MDS into the next round; every partial round then adds ONE constant (to cell
+#     0) and the leftover lands in the constants of the first full round of the second half;
+#   * matrices: a dense D = [[d00, v], [w, Dh]] factors as  S * P  with  S = [[d00, v Dh^-1], [w, I]]  (2t-1 non-trivial
+#     entries) and  P = diag(1, Dh).  P commutes with the partial S-box, so walking the partial rounds from the last one
+#     backwards every round keeps a sparse S and hands its P to the round before it; the final P is folded into the MDS of
+#     the last full round of the first half ("pre-sparse" matrix).
+def _mat_mul(a, b):
+    t = len(a)
+    return [[sum(a[i][k] * b[k][j] for k in range(t)) % R_ for j in range(t)] for i in range(t)]
+
+
+def _mat_inv(a):
+    n = len(a)
+    m = [list(row) + [1 if i == j else 0 for j in range(n)] for i, row in enumerate(a)]
+    for col in range(n):
+        piv = next(r for r in range(col, n) if m[r][col] % R_)
+        m[col], m[piv] = m[piv], m[col]
+        inv = pow(m[col][col], -1, R_)
+        m[col] = [x * inv % R_ for x in m[col]]
+        for r in range(n):
+            if r != col and m[r][col]:
+                f = m[r][col]
+                m[r] = [(x - f * y) % R_ for x, y in zip(m[r], m[col])]
+    return [row[n:] for row in m]
+
+
+def optimized_params(t, mds_mode=MDS_CAUCHY):
+    """dict: rc_full_first[R_F/2][t], pre_sparse[t][t], partial_c0[R_P], sparse[R_P] = (row0[t], col0[t-1]),
+    rc_full_second[R_F/2][t], mds[t][t]."""
+    rc, mds = params(t, mds_mode)
+    rp, half = R_P[t], R_F // 2
+    c = [rc[r * t:(r + 1) * t] for r in range(R_F + rp)]
+    # constants of the partial rounds pushed forward
+    a = []
+    k = list(c[half])
+    for r in range(rp):
+        a.append(k[0])
+        rest = [0] + k[1:]
+        nxt = c[half + r + 1]
+        k = [(nxt[i] + sum(mds[i][j] * rest[j] for j in range(t))) % R_ for i in range(t)]
+    second = [k] + [c[half + rp + 1 + i] for i in range(half - 1)]
+    # sparse factorisation, last partial round first
+    sparse_rev = []
+    d = [row[:] for row in mds]
+    for _ in range(rp):
+        dh = [row[1:] for row in d[1:]]
+        dhi = _mat_inv(dh)
+        v = d[0][1:]
+        vp = [sum(v[k2] * dhi[k2][j] for k2 in range(t - 1)) % R_ for j in range(t - 1)]
+        sparse_rev.append(([d[0][0]] + vp, [d[i][0] for i in range(1, t)]))
+        p = [[1] + [0] * (t - 1)] + [[0] + dh[i] for i in range(t - 1)]
+        d = _mat_mul(p, mds)
+    return {"rc_full_first": c[:half], "pre_sparse": d, "partial_c0": a, "sparse": sparse_rev[::-1],
+            "rc_full_second": second, "mds": mds}
+
+
+_OPT = {}
+
+
+def permute_optimized(state, mds_mode=MDS_CAUCHY):
+    t = len(state)
+    if (t, mds_mode) not in _OPT:
+        _OPT[(t, mds_mode)] = optimized_params(t, mds_mode)
+    o = _OPT[(t, mds_mode)]
+    half = R_F // 2
+    s = list(state)
+
+    def dense(m, x):
+        return [sum(m[i][j] * x[j] for j in range(t)) % R_ for i in range(t)]
+    for r in range(half):
+        s = [pow((x + o["rc_full_first"][r][i]) % R_, 5, R_) for i, x in enumerate(s)]
+        s = dense(o["pre_sparse"] if r == half - 1 else o["mds"], s)
+    for r in range(R_P[t]):
+        s[0] = pow((s[0] + o["partial_c0"][r]) % R_, 5, R_)
+        row0, col0 = o["sparse"][r]
+        n0 = sum(row0[j] * s[j] for j in range(t)) % R_
+        s = [n0] + [(col0[i - 1] * s[0] + s[i]) % R_ for i in range(1, t)]
+    for r in range(half):
+        s = [pow((x + o["rc_full_second"][r][i]) % R_, 5, R_) for i, x in enumerate(s)]
+        s = dense(o["mds"], s)
+    return s

@@ -99,3 +99,51 @@ def test_sanity_ring_counter_and_errors(dclient, tmp_path):
             p.result(5)                                              # the reference would spin forever
     finally:
         p.close()
+
+
+def test_published_permutation_vector_through_cuda(dclient):
+    """The Poseidon reference implementation's test vector (poseidonperm_x5_255_3, tests/golden/external_kats.json)
+    through the SAME kernel template the client's widths use, then random states of widths 9 and 12 (the client's
+    Cauchy-MDS instances) against the oracle's plain-round permutation."""
+    import json
+    import os
+    k = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "external_kats.json")))["poseidon_x5_255_3"]
+    p = PoseidonClient.new(Hash.Poseidon, dclient)
+    try:
+        inp = b"".join(int(x).to_bytes(32, "little") for x in k["input"])
+        out = p.permute(inp, 3, 1)
+        assert [out[32 * i:32 * i + 32][::-1].hex() for i in range(3)] == k["output"]
+        rng = random.Random(5)
+        for t in (3, 9, 12):
+            states = [[rng.randrange(P.R_) for _ in range(t)] for _ in range(40)]
+            states[0] = [0] * t
+            states[1] = [P.R_ - 1] * t
+            blob = b"".join(v.to_bytes(32, "little") for s in states for v in s)
+            got = p.permute(blob, t, 0)
+            for i, s in enumerate(states):
+                exp = P.permute(s)
+                assert [int.from_bytes(got[32 * (i * t + j):32 * (i * t + j + 1)], "little") for j in range(t)] == exp, (t, i)
+    finally:
+        p.close()
+
+
+def test_bulk_tree_height_5_and_device_timer(dclient):
+    """Bulk feed (one set_data for the whole base layer), 4681 records, root recomputed from the returned layer below."""
+    h = 5
+    nbase = num_of_elements_in_base_layer(h)
+    rng = random.Random(23)
+    elems = [rng.randrange(P.R_) for _ in range(11 * nbase)]
+    p = PoseidonClient.new(Hash.Poseidon, dclient)
+    try:
+        p.initialize(PoseidonInitializeParameters(h, TreeMode.TreeC, ""))
+        p.set_data(b"".join(e.to_bytes(32, "little") for e in elems))
+        res = p.result(num_of_elements_oct_tree(h))
+        assert len(res) == num_of_elements_oct_tree(h) and p.device_ms() > 0
+        by = {(r.layer_id, r.hash_id): int.from_bytes(r.hash_byte, "little") for r in res}
+        for i in (0, 1, nbase - 1, 777):
+            assert by[(0, i)] == P.hash_elems(elems[11 * i:11 * i + 11])
+        for l in range(1, h):
+            for i in (0, 8 ** (h - 1 - l) - 1):
+                assert by[(l, i)] == P.hash_elems([by[(l - 1, 8 * i + j)] for j in range(8)])
+    finally:
+        p.close()

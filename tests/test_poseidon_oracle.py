@@ -28,3 +28,35 @@ def test_record_roundtrip_matches_reference_parser():
 def test_tree_sizes():
     assert sum(P.tree_sizes(4)) == 585                               # integration_poseidon.rs:23
     assert P.tree_sizes(4)[0] == 512
+
+
+def test_optimized_evaluation_equals_plain_rounds():
+    """The form the CUDA kernel evaluates (constants pushed forward, sparse partial-round matrices) is the same
+    permutation as round = add constants, S-box, MDS."""
+    import random
+    rng = random.Random(11)
+    for t, mode in ((3, P.MDS_GRAIN), (3, P.MDS_CAUCHY), (9, P.MDS_CAUCHY), (12, P.MDS_CAUCHY)):
+        for _ in range(2):
+            s = [rng.randrange(P.R_) for _ in range(t)]
+            assert P.permute_optimized(s, mode) == P.permute(s, mode)
+
+
+def test_library_host_constants_match_oracle_derivation():
+    """bz_poseidon_optimized_constants (host-only, no device needed): the C++ preprocessing of the product library
+    produces exactly the constants the big-integer derivation gives, for the client's widths and the KAT's."""
+    import ctypes
+    from blaze_b200._lib import lib
+    L = lib()
+    for t, mode in ((3, 1), (3, 0), (9, 0), (12, 0)):
+        n = ctypes.c_size_t()
+        assert L.bz_poseidon_optimized_constants(t, mode, None, 0, ctypes.byref(n)) == 0
+        buf = ctypes.create_string_buffer(n.value)
+        assert L.bz_poseidon_optimized_constants(t, mode, buf, n.value, ctypes.byref(n)) == 0
+        vals = [int.from_bytes(buf.raw[i:i + 32], "little") for i in range(0, n.value, 32)]
+        o = P.optimized_params(t, mode)
+        exp = [x for r in o["rc_full_first"] for x in r] + [x for r in o["mds"] for x in r] + [x for r in o["pre_sparse"] for x in r]
+        for c0, (row0, col0) in zip(o["partial_c0"], o["sparse"]):
+            exp += [c0] + row0 + col0
+        exp += [x for r in o["rc_full_second"] for x in r]
+        assert vals == exp, (t, mode)
+    assert L.bz_poseidon_optimized_constants(5, 0, None, 0, ctypes.byref(n)) != 0
