@@ -56,6 +56,7 @@ SIGNATURES = {
     "bz_msm_sizes": [vp, u32p, u32p, u32p, u32p],
     "bz_msm_phase_times": [vp, ctypes.POINTER(ctypes.c_float)],
     "bz_msm_set_window_bits": [vp, i32],
+    "bz_msm_set_accumulate_mode": [vp, i32, i32],
     "bz_msm_get_api": [vp, u32p, sz],
     "bz_msm_table_build_ms": [vp, ctypes.POINTER(ctypes.c_float)],
     "bz_msm_plan_info": [vp, u32p],

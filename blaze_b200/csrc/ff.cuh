@@ -540,6 +540,165 @@ struct ff {
     return mul(a, o);
   }
 
+  // ---- inversion by division steps (Bernstein & Yang, "Fast constant-time gcd computation and modular inversion",
+  // CHES 2019), on signed 30-bit limbs.  The Fermat inverse below costs ~1.5 N x 32 field products, all on the integer
+  // multiplier pipe; this one costs ~(26 + ...)  batches of 30 division steps, each batch being ~400 plain ALU
+  // instructions plus two small matrix-vector updates (~10 N multiplier instructions) -- about 25x fewer multiplier
+  // instructions.  That is what makes ONE inversion per thread and batch affordable in the batched-affine bucket
+  // accumulation (msm_ba2.cuh): no cross-thread product trees, no extra kernels.
+  //
+  //   divstep(delta, f, g) = (1 - delta, g, (g - f) / 2)              if delta > 0 and g odd
+  //                          (1 + delta, f, (g + (g mod 2) f) / 2)    otherwise
+  // starting from (1, p, x) reaches g = 0 with f = +-1 after at most (49 bits + 57) / 17 steps.  30 steps at a time
+  // are taken on the low words only and collected in a 2x2 matrix T (entries |.| <= 2^30) with
+  // (f, g) <- T (f, g) / 2^30; the same matrix keeps (d, e) with  f = d x,  g = e x  (mod p), the division by 2^30
+  // being made exact by adding the right multiple of p.  At the end x^-1 = f d.
+  static constexpr int NL30 = (32 * N + 2 + 29) / 30;   // 30-bit limbs for values in (-2p, 2p): 9 (256 bits), 13 (384)
+  static constexpr int GCD_MAX_BATCHES = (49 * F::BITS + 57) / 17 / 30 + 1;
+
+  BZ_HDI static void to_signed30(const uint32_t* a, int32_t* o) {
+#pragma unroll
+    for (int j = 0; j < NL30; j++) {
+      const int lo = 30 * j, w = lo >> 5, sh = lo & 31;
+      uint32_t v = w < N ? (a[w] >> sh) : 0u;
+      if (sh > 2 && w + 1 < N) v |= a[w + 1] << (32 - sh);
+      o[j] = (int32_t)(v & 0x3fffffffu);
+    }
+  }
+
+  // 30 division steps on the low words; returns the new delta, T = (u v; q r)
+  BZ_HDI static int32_t divsteps30(int32_t delta, uint32_t f, uint32_t g, int32_t& u, int32_t& v, int32_t& q, int32_t& r) {
+    uint32_t uu = 1, vv = 0, qq = 0, rr = 1;
+#pragma unroll 1
+    for (int i = 0; i < 30; i++) {
+      const uint32_t odd = 0u - (g & 1u);                                  // all ones when g is odd
+      const uint32_t sw = odd & (uint32_t)((int32_t)(0 - delta) >> 31);    // ... and delta > 0: swap
+      // swap: (f, g) <- (g, -f), rows likewise, delta <- -delta
+      const uint32_t nf = (f ^ sw) - sw, nu = (uu ^ sw) - sw, nv = (vv ^ sw) - sw;   // -f, -u, -v when swapping
+      const uint32_t tf = sw ? g : f, tu = sw ? qq : uu, tv = sw ? rr : vv;
+      const uint32_t tg = sw ? nf : g, tq = sw ? nu : qq, tr = sw ? nv : rr;
+      delta = (int32_t)(((uint32_t)delta ^ sw) - sw) + 1;
+      // g <- (g + odd f) / 2, row_g += odd row_f; the f row is doubled instead of halving the g row
+      g = (tg + (tf & odd)) >> 1;
+      qq = tq + (tu & odd);
+      rr = tr + (tv & odd);
+      f = tf;
+      uu = tu << 1;
+      vv = tv << 1;
+    }
+    u = (int32_t)uu; v = (int32_t)vv; q = (int32_t)qq; r = (int32_t)rr;
+    return delta;
+  }
+
+  BZ_HDI static E inv_gcd(const E& a) {
+    constexpr int L = NL30;
+    constexpr int32_t M30 = 0x3fffffff;
+    constexpr uint32_t PINV30 = (0u - F::INV) & 0x3fffffffu;   // p^-1 mod 2^30
+    int32_t f[L], g[L], d[L], e[L], pm[L];
+    {
+      uint32_t pw[N];
+#pragma unroll
+      for (int i = 0; i < N; i++) pw[i] = F::mod()[i];
+      to_signed30(pw, pm);
+    }
+    to_signed30(a.v, g);
+#pragma unroll
+    for (int i = 0; i < L; i++) { f[i] = pm[i]; d[i] = 0; e[i] = 0; }
+    e[0] = 1;
+    int32_t delta = 1;
+#pragma unroll 1
+    for (int it = 0; it < GCD_MAX_BATCHES; it++) {
+      int32_t gz = 0;
+#pragma unroll
+      for (int i = 0; i < L; i++) gz |= g[i];
+      if (gz == 0) break;
+      int32_t u, v, q, r;
+      delta = divsteps30(delta, (uint32_t)f[0] | ((uint32_t)f[1] << 30), (uint32_t)g[0] | ((uint32_t)g[1] << 30), u, v, q, r);
+      // (d, e) <- T (d, e) / 2^30 mod p, kept in (-2p, p)
+      {
+        const int32_t sd = d[L - 1] >> 31, se = e[L - 1] >> 31;
+        int32_t md = (u & sd) + (v & se), me = (q & sd) + (r & se);
+        int64_t cd = (int64_t)u * d[0] + (int64_t)v * e[0];
+        int64_t ce = (int64_t)q * d[0] + (int64_t)r * e[0];
+        md -= (int32_t)((PINV30 * (uint32_t)cd + (uint32_t)md) & (uint32_t)M30);
+        me -= (int32_t)((PINV30 * (uint32_t)ce + (uint32_t)me) & (uint32_t)M30);
+        cd += (int64_t)md * pm[0];
+        ce += (int64_t)me * pm[0];
+        cd >>= 30;
+        ce >>= 30;
+#pragma unroll
+        for (int i = 1; i < L; i++) {
+          cd += (int64_t)u * d[i] + (int64_t)v * e[i] + (int64_t)md * pm[i];
+          ce += (int64_t)q * d[i] + (int64_t)r * e[i] + (int64_t)me * pm[i];
+          d[i - 1] = (int32_t)cd & M30;
+          e[i - 1] = (int32_t)ce & M30;
+          cd >>= 30;
+          ce >>= 30;
+        }
+        d[L - 1] = (int32_t)cd;
+        e[L - 1] = (int32_t)ce;
+      }
+      // (f, g) <- T (f, g) / 2^30 (exact)
+      {
+        int64_t cf = (int64_t)u * f[0] + (int64_t)v * g[0];
+        int64_t cg = (int64_t)q * f[0] + (int64_t)r * g[0];
+        cf >>= 30;
+        cg >>= 30;
+#pragma unroll
+        for (int i = 1; i < L; i++) {
+          cf += (int64_t)u * f[i] + (int64_t)v * g[i];
+          cg += (int64_t)q * f[i] + (int64_t)r * g[i];
+          f[i - 1] = (int32_t)cf & M30;
+          g[i - 1] = (int32_t)cg & M30;
+          cf >>= 30;
+          cg >>= 30;
+        }
+        f[L - 1] = (int32_t)cf;
+        g[L - 1] = (int32_t)cg;
+      }
+    }
+    // x^-1 = f d with f = +-1; bring it to [0, 2p) on the 30-bit limbs, then to 32-bit words
+    const int32_t fneg = f[L - 1] >> 31;
+    int32_t carry = 0;
+#pragma unroll
+    for (int i = 0; i < L; i++) {   // d <- -d when f = -1
+      int32_t t = ((d[i] ^ fneg) - fneg) + carry;
+      if (i < L - 1) { carry = t >> 30; t &= M30; }
+      d[i] = t;
+    }
+    const int32_t dneg = d[L - 1] >> 31;   // d in (-2p, 2p): add p once when negative ...
+    carry = 0;
+#pragma unroll
+    for (int i = 0; i < L; i++) {
+      int32_t t = d[i] + (pm[i] & dneg) + carry;
+      if (i < L - 1) { carry = t >> 30; t &= M30; }
+      d[i] = t;
+    }
+    const int32_t dneg2 = d[L - 1] >> 31;  // ... and once more (d was below -p)
+    carry = 0;
+#pragma unroll
+    for (int i = 0; i < L; i++) {
+      int32_t t = d[i] + (pm[i] & dneg2) + carry;
+      if (i < L - 1) { carry = t >> 30; t &= M30; }
+      d[i] = t;
+    }
+    E y;
+#pragma unroll
+    for (int k = 0; k < N; k++) {   // word k = bits [32k, 32k + 32)
+      const int lo = 32 * k, j = lo / 30, sh = lo - 30 * j;
+      uint32_t w = (uint32_t)d[j] >> sh;
+      if (j + 1 < L) w |= (uint32_t)d[j + 1] << (30 - sh);
+      if (30 - sh + 30 < 32 && j + 2 < L) w |= (uint32_t)d[j + 2] << (60 - sh);
+      y.v[k] = w;
+    }
+    final_sub(y.v);
+    // y = (a R)^-1 as an integer = a^-1 R^-1: two Montgomery products by R^2 give a^-1 R
+    E r2;
+#pragma unroll
+    for (int i = 0; i < N; i++) r2.v[i] = F::r2()[i];
+    return mul(mul(y, r2), r2);
+  }
+
   // a^(p-2): only used once per MSM (result normalisation) and in input generators
   BZ_HDI static E inv(const E& a) {
     uint32_t e[N];

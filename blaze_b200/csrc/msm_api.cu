@@ -377,6 +377,16 @@ extern "C" int32_t bz_msm_set_precompute(bz_msm* m, int32_t mode) {
   for (bz_msm* p : m->parts) { std::lock_guard<std::mutex> lp(p->mu); p->precomp_mode = mode; p->precomp_failed = false; }
   return BZ_OK;
 }
+extern "C" int32_t bz_msm_set_accumulate_mode(bz_msm* m, int32_t mode, int32_t rounds) {
+  if (!m) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null MSMClient");
+  if (mode != -1 && mode != 0 && mode != 2) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "accumulate mode: -1 automatic, 0 XYZZ sweep, 2 batched-affine sweep");
+  if (rounds < -1 || rounds > 8) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "tree rounds must be -1 (automatic) or 0..8");
+  std::lock_guard<std::mutex> lk(m->mu);
+  m->acc_mode = mode;
+  m->acc_rounds = rounds;
+  for (bz_msm* p : m->parts) { std::lock_guard<std::mutex> lp(p->mu); p->acc_mode = mode; p->acc_rounds = rounds; }
+  return BZ_OK;
+}
 extern "C" int32_t bz_msm_set_raw_result(bz_msm* m, int32_t raw) {
   if (!m) return fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null MSMClient");
   std::lock_guard<std::mutex> lk(m->mu);
@@ -396,7 +406,8 @@ extern "C" int32_t bz_msm_plan_info_ex(bz_msm* m, uint32_t out[8]) {
   out[4] = p->plan.W;         // bucket sets (1 when the windows are merged)
   out[5] = p->plan.merged;
   out[6] = (uint32_t)(p->wtable_bytes >> 20);   // MiB held by the window-merged table
-  out[7] = p->plan.fb | (p->plan.rest << 8) | (p->plan.nlev << 16);
+  out[7] = p->plan.fb | (p->plan.rest << 8) | (p->plan.nlev << 16) | (p->plan.batch_affine << 24) |
+           ((p->plan.batch_affine == 2 ? p->plan.ba_rounds : 0) << 28);
   return BZ_OK;
 }
 extern "C" int32_t bz_msm_plan_info(bz_msm* m, uint32_t out[4]) {

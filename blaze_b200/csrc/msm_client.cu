@@ -28,6 +28,13 @@ using namespace bz;
 
 #define fail bz_fail
 
+#ifndef BZ_MSM_BA2_DEFAULT
+#define BZ_MSM_BA2_DEFAULT 1
+#endif
+#ifndef BZ_BA2_CTAS_PER_SM
+#define BZ_BA2_CTAS_PER_SM 3     // = BZ_BA2_MINBLOCKS of msm_ba2.cuh
+#endif
+
 // ------------------------------------------------------------------------------------ MSM planning
 static const CurveOps* ops_for(int curve) {
   switch (curve) {
@@ -115,7 +122,7 @@ static size_t ws_bytes_estimate(const bz_msm* m, uint64_t total, int c, int W) {
 
 static int32_t make_plan(bz_msm* m, uint64_t M, int words_per_scalar, bool merged) {
   if (m->have_plan && m->plan.M == M && m->plan.words_per_scalar == words_per_scalar && (m->plan.merged != 0) == merged &&
-      (m->forced_c == 0 || m->forced_c == m->plan.c))
+      (m->forced_c == 0 || m->forced_c == m->plan.c) && m->plan.acc_mode_req == m->acc_mode && m->plan.acc_rounds_req == m->acc_rounds)
     return BZ_OK;
   ws_free(m);
   size_t mem_free = 0, mem_total = 0;
@@ -180,6 +187,13 @@ static int32_t make_plan(bz_msm* m, uint64_t M, int words_per_scalar, bool merge
   }
   p.batch_affine = 0;
   if (const char* e = getenv("BZ_MSM_BA")) p.batch_affine = (atoi(e) && !merged) ? 1 : 0;
+  int ba2_env = -1, ba2_rounds_env = -1;
+  if (const char* e = getenv("BZ_MSM_BA2")) ba2_env = atoi(e);
+  if (const char* e = getenv("BZ_MSM_BA2_ROUNDS")) ba2_rounds_env = atoi(e);
+  if (m->acc_mode >= 0) { ba2_env = m->acc_mode == 2 ? 1 : 0; if (m->acc_mode != 1) p.batch_affine = 0; }
+  if (m->acc_rounds >= 0) ba2_rounds_env = m->acc_rounds;
+  p.acc_mode_req = m->acc_mode;
+  p.acc_rounds_req = m->acc_rounds;
   p.tma_stage = 0;
   if (const char* e = getenv("BZ_MSM_TMA")) p.tma_stage = atoi(e) ? 1 : 0;
   p.c = best_c;
@@ -214,6 +228,25 @@ static int32_t make_plan(bz_msm* m, uint64_t M, int words_per_scalar, bool merge
   if (const char* e = getenv("BZ_MSM_SEG")) L = (uint32_t)std::max(1, atoi(e));
   p.seg_len = L;
   p.nseg = (total + L - 1) / L;
+  // Fused batched-affine sweep (msm_ba2.cuh): pays when the bucket runs inside a segment are long enough to offer a few
+  // dozen independent additions per tree round; otherwise the XYZZ sweep.
+  if (!p.batch_affine) {
+    const double avg = (double)total / ((double)p.W * (double)p.nb);   // entries per bucket (upper bound: zero digits drop out)
+    const bool want = ba2_env >= 0 ? ba2_env != 0 : (BZ_MSM_BA2_DEFAULT && avg >= 16.0 && L >= 64);
+    if (want && L >= 4) {
+      int r = 0;
+      while ((2.0 * (double)(1u << r)) <= std::min(avg, (double)L)) r++;   // floor(log2(min(avg, L)))
+      r = std::max(1, std::min(4, r - 2));
+      if (ba2_rounds_env >= 0) r = std::min(ba2_rounds_env, 8);
+      p.batch_affine = 2;
+      p.ba_rounds = r;
+      p.ba_cap = L / 2 + 32;
+      int sms = 148;
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->dc->device);
+      const uint64_t want_ctas = (uint64_t)sms * BZ_BA2_CTAS_PER_SM;
+      p.ba_ctas = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(want_ctas, (p.nseg + 127) / 128));
+    }
+  }
   // reduction chunk (k_reduce_level): 16 buckets per thread, 8 when that leaves the machine underfilled
   p.chunk = ((uint64_t)p.W * p.nvalues / 16 < 148ull * 256) ? 8 : 16;
   if (const char* e = getenv("BZ_MSM_CHUNK")) {
@@ -281,6 +314,11 @@ static int32_t make_plan(bz_msm* m, uint64_t M, int words_per_scalar, bool merge
     A(&m->ws.ba_lvl[2], n3 * fb);
     A((uint8_t**)&m->ws.ba_buf1, S1 * ab);
     A((uint8_t**)&m->ws.ba_buf0, S2 * ab);
+  }
+  if (p.batch_affine == 2) {
+    // three arrays (x, y, running products) of ba_cap slots per lane, one set per resident warp
+    const size_t per_warp = (size_t)3 * p.ba_cap * (m->ops->fq_bytes) * 32;
+    A((uint8_t**)&m->ws.ba2_scratch, per_warp * p.ba_ctas * 4);
   }
   A((uint8_t**)&m->ws.red_a, (size_t)2 * p.W * p.nchunks * xb);        // S and V of the even levels
   A((uint8_t**)&m->ws.red_b, (size_t)2 * p.W * (nch1 + 1) * xb);       // ... of the odd levels

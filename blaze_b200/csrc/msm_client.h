@@ -43,6 +43,7 @@ struct bz_msm {
   uint64_t hbm_addr = 0, hbm_off = 0;
   uint32_t next_label = 0, last_label = 0;
   int forced_c = 0;
+  int acc_mode = -1, acc_rounds = -1;   // bz_msm_set_accumulate_mode: -1 automatic
   // task state machine
   int pending_tasks = 0;     // start_process() calls not yet matched with data
   bool data_ready = false;   // set_data() arrived, not yet consumed by a task
@@ -121,6 +122,7 @@ int32_t leaf_load_data_to_hbm(bz_msm* m, const uint8_t* points, size_t len, uint
 int32_t leaf_generate_chain_points(bz_msm* m, const uint8_t* p0q, size_t p0q_len, uint64_t first, uint64_t n, uint64_t addr,
                                    uint64_t offset);
 int32_t leaf_phase_times(bz_msm* m, float ms[4]);
+
 int32_t leaf_combine_results(bz_msm* m, const uint8_t* records, int32_t n, uint8_t* out, size_t out_len);
 // make sure m->comb_dev holds at least `bytes`
 int32_t leaf_comb_reserve(bz_msm* m, size_t bytes);

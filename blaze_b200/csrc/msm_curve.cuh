@@ -17,24 +17,10 @@
 
 #include "ec.cuh"
 #include "msm_internal.h"
+#include "msm_types.cuh"
+#include "msm_ba2.cuh"
 
 namespace bz {
-
-template <class C>
-struct alignas(16) AffineM {   // packed affine point (lists that are read sequentially)
-  uint32_t x[C::Fq::N], y[C::Fq::N];
-};
-// Entry of the resident Montgomery point table, which is only ever GATHERED: 96-byte records are padded to
-// 128 B so that one gather touches exactly one 128-byte DRAM line (unpadded they straddle two lines half
-// of the time: measured 197 B of DRAM traffic per 96-B record, profiles/r1_traffic.json).
-template <class C>
-struct alignas((sizeof(uint32_t) * 2 * C::Fq::N == 96) ? 128 : 16) AffineT {
-  uint32_t x[C::Fq::N], y[C::Fq::N];
-};
-template <class C>
-struct alignas(16) XyzzM {
-  uint32_t X[C::Fq::N], Y[C::Fq::N], ZZ[C::Fq::N], ZZZ[C::Fq::N];
-};
 
 template <class C>
 struct dev {
@@ -657,12 +643,16 @@ struct CurveLaunch {
   static void bucket_phase(const MsmPlan& p, const MsmWorkspace& ws, const void* table, cudaStream_t st) {
     const uint32_t ngoff = (uint32_t)p.W * p.nb;
     XyzzM<C>* buckets = (XyzzM<C>*)ws.buckets;
-    if (!p.batch_affine) cudaMemsetAsync(buckets, 0, (size_t)ngoff * sizeof(XyzzM<C>), st);
-    if (p.batch_affine) {
+    if (p.batch_affine != 1) cudaMemsetAsync(buckets, 0, (size_t)ngoff * sizeof(XyzzM<C>), st);
+    if (p.batch_affine == 1) {
       ba_bucket_phase_fwd<C>(p, ws, table, st);
     } else {
     if (ws.ev_acc0) cudaEventRecord(ws.ev_acc0, st);
-    if (p.tma_stage) {
+    if (p.batch_affine == 2) {
+      k_accumulate_ba<C><<<p.ba_ctas, 128, 0, st>>>((const AffineT<C>*)table, ws.sorted, ws.goff, buckets, ws.part_id,
+                                                   (XyzzM<C>*)ws.part_pt, p.nseg, p.seg_len, ngoff, p.ba_rounds,
+                                                   (uint4*)ws.ba2_scratch, p.ba_cap);
+    } else if (p.tma_stage) {
       const size_t smem = (size_t)4 * 2 * 32 * BZ_ACC_RING_STRIDE + 4 * 2 * sizeof(uint64_t);
       k_accumulate_tma<C><<<(unsigned)((p.nseg + 127) / 128), 128, smem, st>>>(
           (const AffineT<C>*)table, ws.sorted, ws.goff, buckets, ws.part_id, (XyzzM<C>*)ws.part_pt, p.nseg, p.seg_len,

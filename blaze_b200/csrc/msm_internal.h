@@ -62,7 +62,12 @@ struct MsmPlan {
   uint64_t nseg;           // number of accumulate segments = ceil(W*M / seg_len)
   int raw_result;          // 1: result record left projective (Z != 1): shard of a multi-GPU MSM, normalised by the combine
   int tma_stage;           // 1: k_accumulate_tma (points staged through shared memory by cp.async.bulk), 0: register prefetch
-  int batch_affine;        // 1: accumulate buckets by batched affine addition (msm_ba.cuh), 0: XYZZ sweep
+  int batch_affine;        // 0: XYZZ sweep (k_accumulate); 2: fused batched-affine sweep (msm_ba2.cuh, k_accumulate_ba);
+                           // 1: round 1's multi-kernel batched-affine phases (msm_ba.cuh, opt-in, kept for comparison)
+  int ba_rounds;           // batch_affine == 2: tree rounds per segment before the XYZZ fold
+  uint32_t ba_cap;         //                    scratch slots per lane
+  uint32_t ba_ctas;        //                    persistent grid size
+  int acc_mode_req, acc_rounds_req;   // what the client asked for when the plan was made (-1 = automatic)
   uint32_t chunk;          // entries per reduce thread at every level of the running-sum recursion (power of two)
   uint32_t nchunks;        // ceil(nb / chunk): level-0 chunk count
   DigitConst dc;
@@ -96,6 +101,7 @@ struct MsmWorkspace {
   uint32_t* ba_lvlp[2];           //                      prefix / inverse arrays per level
   void* ba_buf0;                  // affine lists of the even rounds (>= 2): (total/4 + W nb) entries
   void* ba_buf1;                  // affine lists of the odd rounds: (total/2 + W nb) entries
+  void* ba2_scratch;              // batch_affine == 2: per-warp affine lists + running products
   cudaEvent_t ev_acc0, ev_acc1;   // bracket the accumulate kernel alone (roofline timing); may be null
 };
 

@@ -179,7 +179,13 @@ class MSMClient(DriverPrimitive):
         out = (ctypes.c_uint32 * 8)()
         check(lib().bz_msm_plan_info_ex(self._h, out))
         return {"c": out[0], "windows": out[1], "buckets_per_window": out[2], "segment": out[3],
-                "bucket_sets": out[4], "merged_table": bool(out[5]), "merged_table_mib": out[6]}
+                "bucket_sets": out[4], "merged_table": bool(out[5]), "merged_table_mib": out[6],
+                "accumulate": {0: "xyzz", 1: "batched-affine (multi-kernel)", 2: "batched-affine"}[(out[7] >> 24) & 0xF],
+                "ba_rounds": (out[7] >> 28) & 0xF}
+
+    def set_accumulate_mode(self, mode=-1, rounds=-1):
+        """-1 automatic, 0 XYZZ mixed-add sweep, 2 fused batched-affine sweep (`rounds` tree rounds, -1 automatic)."""
+        check(lib().bz_msm_set_accumulate_mode(self._h, int(mode), int(rounds)))
 
     def set_precompute(self, mode):
         """Window-merged table for HBM-resident points: 0 never, 1 from the second MSM on the same points

@@ -139,10 +139,14 @@ int32_t bz_msm_set_window_bits(bz_msm* m, int32_t c);
 int32_t bz_msm_get_api(bz_msm* m, uint32_t* regs, size_t n_words);
 /* milliseconds the last build of the window-merged table took (0 if none was built) */
 int32_t bz_msm_table_build_ms(bz_msm* m, float* ms);
+/* bucket-accumulation kernel: -1 (default) chosen per task from the bucket sizes, 0 the XYZZ mixed-add sweep, 2 the
+ * fused batched-affine sweep; `rounds` = tree rounds of the latter (-1 automatic).  Same results in every mode. */
+int32_t bz_msm_set_accumulate_mode(bz_msm* m, int32_t mode, int32_t rounds);
 /* plan of the last launched task: c, W, buckets/window, segment length */
 int32_t bz_msm_plan_info(bz_msm* m, uint32_t out[4]);
 /* extended plan: c, digit windows (mixed adds per scalar), buckets/set, segment length, bucket sets,
- * merged flag, MiB held by the window-merged table, level-2 sort bits */
+ * merged flag, MiB held by the window-merged table, [7] = final sort bits | partition bits << 8 | levels << 16 |
+ * accumulate mode << 24 | batched-affine tree rounds << 28 */
 int32_t bz_msm_plan_info_ex(bz_msm* m, uint32_t out[8]);
 /* Window-merged table for HBM-resident point sets ("precomputed points resident in HBM"): the client
  * derives 2^(c w) * P_i for every digit window w from the points written with load_data_to_hbm

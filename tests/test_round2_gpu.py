@@ -484,3 +484,80 @@ def test_precompute_x8_hbm_mode_at_scale(dclient, oracle):
         assert m.plan_info()["windows"] >= 1
     finally:
         m.close()
+
+
+# ------------------------------------------------------------------------------------------ batched-affine sweep
+@pytest.mark.parametrize("cname,curve", [("BLS12_381", Curve.BLS381), ("BN254", Curve.BN254), ("BLS12_377", Curve.BLS377)])
+@pytest.mark.parametrize("rounds", [1, 3, 5])
+def test_batched_affine_sweep_vs_oracle(dclient, oracle, cname, curve, rounds):
+    """The fused batched-affine accumulation (msm_ba2.cuh) forced on, against the oracle: uniform scalars at two window
+    sizes (long and short bucket runs), the reference's tiled distribution (every first-round pair is a doubling),
+    and skewed scalars (one giant bucket per window; mostly empty buckets)."""
+    from util import tile
+    c = CURVE_BY_NAME[cname]
+    n = 6000
+    pts, _, _ = chain_points(c, n, seed=17)
+    sc = random_scalars(c, n, seed=18)
+    exp = oracle.msm_pippenger(cname, pts, sc, n)
+    for cb in (5, 9):
+        m = MSMClient.new(MSMInit(PointMemoryType.DMA, False, curve), dclient)
+        try:
+            m.set_window_bits(cb)
+            m.set_accumulate_mode(2, rounds)
+            params = MSMParams(n, None)
+            m.initialize(params)
+            m.start_process()
+            m.set_data(MSMInput(pts, sc, params))
+            m.wait_result()
+            assert m.result().result == exp
+            assert m.plan_info()["accumulate"] == "batched-affine" and m.plan_info()["ba_rounds"] == rounds
+        finally:
+            m.close()
+    pts256, _, _ = chain_points(c, 256, seed=11)
+    sc256 = random_scalars(c, 256, seed=12)
+    nt = 256 * 41 + 7
+    tp, ts = tile(pts256, c.point_size, 256, nt), tile(sc256, 32, 256, nt)
+    same = np.frombuffer((0x1d3c5b7a99f0e1d2c3b4a5968778695a4b3c2d1e0f).to_bytes(32, "little") * n, dtype=np.uint8).copy()
+    few = np.zeros(n * 32, dtype=np.uint8)
+    few[32 * 100:32 * 100 + 31] = 0xAB
+    few[32 * 4000:32 * 4000 + 8] = 0x77
+    for p_, s_, k in ((tp, ts, nt), (pts, same, n), (pts, few, n)):
+        m = MSMClient.new(MSMInit(PointMemoryType.DMA, False, curve), dclient)
+        try:
+            m.set_window_bits(7)
+            m.set_accumulate_mode(2, rounds)
+            params = MSMParams(k, None)
+            m.initialize(params)
+            m.start_process()
+            m.set_data(MSMInput(p_, s_, params))
+            m.wait_result()
+            assert m.result().result == oracle.msm_pippenger(cname, p_, s_, k)
+        finally:
+            m.close()
+
+
+def test_batched_affine_merged_table_2p20_matches_xyzz(dclient, oracle):
+    """HBM-resident points with the window-merged table at 2^20: automatic mode picks the batched-affine sweep; result
+    equals the closed form and the XYZZ sweep's bytes."""
+    c = CURVE_BY_NAME["BLS12_381"]
+    n = 1 << 20
+    p0, q = seed_points(c, 21)
+    m = MSMClient.new(MSMInit(PointMemoryType.HBM, False, Curve.BLS381), dclient)
+    try:
+        m.generate_chain_points(p0 + q, 0, n, 0x40_0000_0000, 0)
+        m.set_precompute(2)
+        params = MSMParams(n, (0x40_0000_0000, 0))
+        sc = random_scalars(c, n, seed=22)
+        res = {}
+        for mode in (-1, 0, 2):
+            m.set_accumulate_mode(mode, -1)
+            m.initialize(params)
+            m.start_process()
+            m.set_data(MSMInput(None, sc, params))
+            m.wait_result()
+            res[mode] = (m.result().result, m.plan_info())
+        exp = oracle.chain_expected("BLS12_381", p0, q, sc, n)
+        assert res[-1][0] == exp and res[0][0] == exp and res[2][0] == exp
+        assert res[0][1]["accumulate"] == "xyzz" and res[2][1]["accumulate"] == "batched-affine"
+    finally:
+        m.close()
