@@ -400,6 +400,14 @@ struct ff {
   static __device__ __noinline__ E mul_call(const E a, const E b) { return mul_sel(a, b); }
   static __device__ __noinline__ E sqr_call(const E a) { return sqr_inline(a); }
   static __device__ __noinline__ E mul2_call(const E a, const E b, const E c, const E d) { return mul2_sel(a, b, c, d); }
+  // out-of-line add / sub / inverse for code whose loops would otherwise outgrow the instruction cache (msm_ba2.cuh)
+  static __device__ __noinline__ E sub_call(const E a, const E b) { return sub(a, b); }
+  static __device__ __noinline__ E add_call(const E a, const E b) { return add(a, b); }
+  static __device__ __noinline__ E inv_gcd_call(const E a) { return inv_gcd(a); }
+#else
+  static E sub_call(const E& a, const E& b) { return sub(a, b); }
+  static E add_call(const E& a, const E& b) { return add(a, b); }
+  static E inv_gcd_call(const E& a) { return inv_gcd(a); }
 #endif
   BZ_HDI static E mul_sel(const E& a, const E& b) {
 #ifdef BZ_KARATSUBA

@@ -132,6 +132,51 @@ struct ba2 {
     for (int k = 0; k < N; k++) { dst->X[k] = acc.X.v[k]; dst->Y[k] = acc.Y.v[k]; dst->ZZ[k] = acc.ZZ.v[k]; dst->ZZZ[k] = acc.ZZZ.v[k]; }
   }
 
+  // ---- affine + affine given the inverse of the denominator (ec<C>::ba_classify / ba_finish with the additions and
+  // subtractions out of line: the backward loop stays small enough for the instruction cache)
+  BZ_HDI static E sub_(const E& a, const E& b) { return F::sub_call(a, b); }
+  BZ_HDI static int classify(const Affine<C>& p1, const Affine<C>& p2, E& den) {
+    if (G::is_identity(p1)) { den = F::one(); return 2; }
+    if (G::is_identity(p2)) { den = F::one(); return 3; }
+    den = sub_(p2.x, p1.x);
+    if (!F::is_zero(den)) return 0;
+    if (F::is_zero(F::add_call(p1.y, p2.y))) { den = F::one(); return 4; }   // also covers y == 0
+    den = F::add_call(p1.y, p1.y);
+    return 1;
+  }
+  BZ_HDI static Affine<C> finish(int kind, const Affine<C>& p1, const Affine<C>& p2, const E& inv_den) {
+    if (kind == 2) return p2;
+    if (kind == 3) return p1;
+    Affine<C> r;
+    if (kind == 4) { r.x = F::zero(); r.y = F::zero(); return r; }
+    E lam;
+    if (kind == 0) {
+      lam = F::mul(sub_(p2.y, p1.y), inv_den);
+    } else {
+      const E x2 = F::sqr(p1.x);
+      lam = F::mul(F::add_call(F::add_call(x2, x2), x2), inv_den);
+    }
+    r.x = sub_(sub_(F::sqr(lam), p1.x), p2.x);
+    r.y = sub_(F::mul(lam, sub_(p1.x, r.x)), p1.y);
+    return r;
+  }
+
+  // bring operand i of round r's input list towards the SM ahead of its use (table line, or the lane's scratch pieces)
+  BZ_HDI static void prefetch_in(const Ctx& c, int r, uint32_t i, bool with_y) {
+#ifdef __CUDACC__
+    if (r == 0) {
+      const uint32_t ent = __ldg(c.sorted + c.s + i);
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(c.table[ent & 0x7fffffffu].x));
+    } else {
+#pragma unroll
+      for (int k = 0; k < NQ; k++) {
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(c.sx + ((size_t)i * NQ + k) * 32));
+        if (with_y) asm volatile("prefetch.global.L1 [%0];" ::"l"(c.sy + ((size_t)i * NQ + k) * 32));
+      }
+    }
+#endif
+  }
+
   // one segment.  `rounds` tree rounds of batched affine additions, then an XYZZ fold of what is left of every run.
   BZ_HDI static void segment(Ctx& c, uint64_t t, int rounds, XyzzM<C>* buckets, uint32_t* part_id, XyzzM<C>* part_pt) {
     uint32_t id0 = 0xffffffffu, id1 = 0xffffffffu;
@@ -151,6 +196,7 @@ struct ba2 {
       // ---- forward, last slot first: running product of the pair denominators
       uint32_t I = 0, O = 0;
       for (uint32_t g = c.g_first; g <= g_last; g++) { const uint32_t n = run_len(c, g, r); I += n; O += (n + 1) >> 1; }
+      if (I == O) { rounds = r; break; }   // every run is down to one entry: the list stays where round r-1 left it
       E prod = F::one();
       uint32_t npairs = 0;
       {
@@ -166,12 +212,14 @@ struct ba2 {
             j = (int32_t)((n + 1) >> 1) - 1;
             continue;
           }
+          const uint32_t i1 = Ib + 2 * j;
+          if (i1 >= 4) { prefetch_in(c, r, i1 - 3, false); prefetch_in(c, r, i1 - 4, false); }   // two slots ahead (descending)
           if (2u * (uint32_t)j + 1 < n) {
-            const E x1 = in_x(c, r, Ib + 2 * j), x2 = in_x(c, r, Ib + 2 * j + 1);
-            E den = F::sub(x2, x1);
+            const E x1 = in_x(c, r, i1), x2 = in_x(c, r, i1 + 1);
+            E den = sub_(x2, x1);
             if (F::is_zero(x1) || F::is_zero(x2) || F::is_zero(den)) {   // identity operand, tangent or cancellation
-              const Affine<C> p1 = in_pt(c, r, Ib + 2 * j), p2 = in_pt(c, r, Ib + 2 * j + 1);
-              G::ba_classify(p1, p2, den);
+              const Affine<C> p1 = in_pt(c, r, i1), p2 = in_pt(c, r, i1 + 1);
+              classify(p1, p2, den);
             }
             st_s(c.sp, Ob + j, prod);
             prod = F::mul(prod, den);
@@ -180,7 +228,7 @@ struct ba2 {
           j--;
         }
       }
-      E inv = npairs ? F::inv_gcd(prod) : F::one();
+      E inv = npairs ? F::inv_gcd_call(prod) : F::one();
       // ---- backward, first slot first: peel the inverses off and finish the additions, in place
       {
         uint32_t g = c.g_first, n = run_len(c, g, r), Ib = 0, Ob = 0, j = 0, cnt = (n + 1) >> 1;
@@ -195,14 +243,16 @@ struct ba2 {
             j = 0;
             continue;
           }
-          const Affine<C> p1 = in_pt(c, r, Ib + 2 * j);
+          const uint32_t i1 = Ib + 2 * j;
+          if (i1 + 5 < I) { prefetch_in(c, r, i1 + 4, true); prefetch_in(c, r, i1 + 5, true); }   // two slots ahead
+          const Affine<C> p1 = in_pt(c, r, i1);
           if (2 * j + 1 < n) {
-            const Affine<C> p2 = in_pt(c, r, Ib + 2 * j + 1);
+            const Affine<C> p2 = in_pt(c, r, i1 + 1);
             E den;
-            const int kind = G::ba_classify(p1, p2, den);
+            const int kind = classify(p1, p2, den);
             const E dinv = F::mul(inv, ld_s(c.sp, Ob + j));
             inv = F::mul(inv, den);
-            const Affine<C> sum = G::ba_finish(kind, p1, p2, dinv);
+            const Affine<C> sum = finish(kind, p1, p2, dinv);
             st_s(c.sx, Ob + j, sum.x);
             st_s(c.sy, Ob + j, sum.y);
           } else {
@@ -213,19 +263,25 @@ struct ba2 {
         }
       }
     }
-    // ---- what is left of every run: XYZZ mixed adds, then the bucket (or the segment's head / tail partial)
+    // ---- what is left of every run: XYZZ mixed adds, then the bucket (or the segment's head / tail partial).  ONE flat
+    // loop over the remaining entries (lanes of a warp hold different run structures: nested loops would serialise them)
     {
-      uint32_t Ib = 0;
-      for (uint32_t g = c.g_first; g <= g_last; g++) {
-        const uint32_t n = run_len(c, g, rounds);
-        if (!n) continue;
-        XYZZ<C> acc = G::infinity();
-        for (uint32_t j = 0; j < n; j++) {
-          const Affine<C> a = in_pt(c, rounds, Ib + j);
-          G::madd(acc, a);
+      uint32_t g = c.g_first, n = run_len(c, g, rounds), Ib = 0, j = 0;
+      XYZZ<C> acc = G::infinity();
+      for (;;) {
+        if (j == n) {
+          if (n) store_run(c, t, g, acc, buckets, part_pt, id0, id1);
+          if (g == g_last) break;
+          Ib += n;
+          g++;
+          n = run_len(c, g, rounds);
+          j = 0;
+          acc = G::infinity();
+          continue;
         }
-        Ib += n;
-        store_run(c, t, g, acc, buckets, part_pt, id0, id1);
+        const Affine<C> a = in_pt(c, rounds, Ib + j);
+        G::madd(acc, a);
+        j++;
       }
     }
     part_id[2 * t] = id0;

@@ -29,7 +29,10 @@ using namespace bz;
 #define fail bz_fail
 
 #ifndef BZ_MSM_BA2_DEFAULT
-#define BZ_MSM_BA2_DEFAULT 1
+#define BZ_MSM_BA2_DEFAULT 0   // measured slower than the XYZZ sweep on B200 (profiles/r2_ncu_k_accumulate_ba_2p22.txt): opt-in
+#endif
+#ifndef BZ_MSM_SEG_MAX
+#define BZ_MSM_SEG_MAX 256
 #endif
 #ifndef BZ_BA2_CTAS_PER_SM
 #define BZ_BA2_CTAS_PER_SM 3     // = BZ_BA2_MINBLOCKS of msm_ba2.cuh
@@ -122,7 +125,7 @@ static size_t ws_bytes_estimate(const bz_msm* m, uint64_t total, int c, int W) {
 
 static int32_t make_plan(bz_msm* m, uint64_t M, int words_per_scalar, bool merged) {
   if (m->have_plan && m->plan.M == M && m->plan.words_per_scalar == words_per_scalar && (m->plan.merged != 0) == merged &&
-      (m->forced_c == 0 || m->forced_c == m->plan.c) && m->plan.acc_mode_req == m->acc_mode && m->plan.acc_rounds_req == m->acc_rounds)
+      (m->forced_c == 0 || m->forced_c == m->plan.c))
     return BZ_OK;
   ws_free(m);
   size_t mem_free = 0, mem_total = 0;
@@ -187,13 +190,7 @@ static int32_t make_plan(bz_msm* m, uint64_t M, int words_per_scalar, bool merge
   }
   p.batch_affine = 0;
   if (const char* e = getenv("BZ_MSM_BA")) p.batch_affine = (atoi(e) && !merged) ? 1 : 0;
-  int ba2_env = -1, ba2_rounds_env = -1;
-  if (const char* e = getenv("BZ_MSM_BA2")) ba2_env = atoi(e);
-  if (const char* e = getenv("BZ_MSM_BA2_ROUNDS")) ba2_rounds_env = atoi(e);
-  if (m->acc_mode >= 0) { ba2_env = m->acc_mode == 2 ? 1 : 0; if (m->acc_mode != 1) p.batch_affine = 0; }
-  if (m->acc_rounds >= 0) ba2_rounds_env = m->acc_rounds;
-  p.acc_mode_req = m->acc_mode;
-  p.acc_rounds_req = m->acc_rounds;
+
   p.tma_stage = 0;
   if (const char* e = getenv("BZ_MSM_TMA")) p.tma_stage = atoi(e) ? 1 : 0;
   p.c = best_c;
@@ -222,31 +219,13 @@ static int32_t make_plan(bz_msm* m, uint64_t M, int words_per_scalar, bool merge
     p.nvalues = p.nb;
   }
   uint64_t total = (uint64_t)p.W * Ms;
-  // segment length: enough threads to fill the machine several times over, at most 256 entries each
-  uint32_t L = 256;
+  // segment length: enough threads to fill the machine several times over, at most BZ_MSM_SEG_MAX entries each (measured
+  // at 2^26: 256 -> 248.6 ms accumulate + 14.3 ms tail, 1024 -> 255.5 + 13.2)
+  uint32_t L = BZ_MSM_SEG_MAX;
   while (L > 16 && total / L < 148ull * 256 * 8) L >>= 1;
   if (const char* e = getenv("BZ_MSM_SEG")) L = (uint32_t)std::max(1, atoi(e));
   p.seg_len = L;
   p.nseg = (total + L - 1) / L;
-  // Fused batched-affine sweep (msm_ba2.cuh): pays when the bucket runs inside a segment are long enough to offer a few
-  // dozen independent additions per tree round; otherwise the XYZZ sweep.
-  if (!p.batch_affine) {
-    const double avg = (double)total / ((double)p.W * (double)p.nb);   // entries per bucket (upper bound: zero digits drop out)
-    const bool want = ba2_env >= 0 ? ba2_env != 0 : (BZ_MSM_BA2_DEFAULT && avg >= 16.0 && L >= 64);
-    if (want && L >= 4) {
-      int r = 0;
-      while ((2.0 * (double)(1u << r)) <= std::min(avg, (double)L)) r++;   // floor(log2(min(avg, L)))
-      r = std::max(1, std::min(4, r - 2));
-      if (ba2_rounds_env >= 0) r = std::min(ba2_rounds_env, 8);
-      p.batch_affine = 2;
-      p.ba_rounds = r;
-      p.ba_cap = L / 2 + 32;
-      int sms = 148;
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->dc->device);
-      const uint64_t want_ctas = (uint64_t)sms * BZ_BA2_CTAS_PER_SM;
-      p.ba_ctas = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(want_ctas, (p.nseg + 127) / 128));
-    }
-  }
   // reduction chunk (k_reduce_level): 16 buckets per thread, 8 when that leaves the machine underfilled
   p.chunk = ((uint64_t)p.W * p.nvalues / 16 < 148ull * 256) ? 8 : 16;
   if (const char* e = getenv("BZ_MSM_CHUNK")) {
@@ -315,18 +294,16 @@ static int32_t make_plan(bz_msm* m, uint64_t M, int words_per_scalar, bool merge
     A((uint8_t**)&m->ws.ba_buf1, S1 * ab);
     A((uint8_t**)&m->ws.ba_buf0, S2 * ab);
   }
-  if (p.batch_affine == 2) {
-    // three arrays (x, y, running products) of ba_cap slots per lane, one set per resident warp
-    const size_t per_warp = (size_t)3 * p.ba_cap * (m->ops->fq_bytes) * 32;
-    A((uint8_t**)&m->ws.ba2_scratch, per_warp * p.ba_ctas * 4);
-  }
   A((uint8_t**)&m->ws.red_a, (size_t)2 * p.W * p.nchunks * xb);        // S and V of the even levels
   A((uint8_t**)&m->ws.red_b, (size_t)2 * p.W * (nch1 + 1) * xb);       // ... of the odd levels
   A(&m->ws.err, 16);
   A(&m->ws.result, 256);
   if (e != cudaSuccess) {
     ws_free(m);
-    return fail(BZ_ERR_WRITE, "workspace allocation failed for M=%llu c=%d: %s", (unsigned long long)M, p.c, cudaGetErrorString(e));
+    size_t f = 0, t = 0;
+    cudaMemGetInfo(&f, &t);
+    return fail(BZ_ERR_WRITE, "workspace allocation failed for M=%llu c=%d merged=%d: %s (%zu MiB of %zu MiB free)", (unsigned long long)M, p.c,
+                (int)merged, cudaGetErrorString(e), f >> 20, t >> 20);
   }
   (void)ilog2_floor;
   m->plan = p;
@@ -381,6 +358,7 @@ int32_t bz::leaf_free(bz_msm* m) {
   wtable_free(m);
   if (m->dma_points) cudaFree(m->dma_points);
   if (m->comb_dev) cudaFree(m->comb_dev);
+  if (m->ba2_scratch) cudaFree(m->ba2_scratch);
   for (int b = 0; b < 2; b++) {
     if (m->scalars_dev[b]) cudaFree(m->scalars_dev[b]);
     if (m->ev_copied[b]) cudaEventDestroy(m->ev_copied[b]);
@@ -462,6 +440,51 @@ int32_t bz::leaf_comb_reserve(bz_msm* m, size_t bytes) {
   return BZ_OK;
 }
 
+// Which bucket-accumulation kernel this task uses (decided per task: it does not touch the workspace, only the scratch of
+// the batched-affine sweep, which is allocated on first use).  Fused batched-affine sweep (msm_ba2.cuh): pays when the
+// bucket runs inside a segment are long enough to offer a few dozen independent additions per tree round.
+static int32_t plan_accumulate(bz_msm* m) {
+  MsmPlan& p = m->plan;
+  if (p.batch_affine == 1) return BZ_OK;   // round 1's multi-kernel phases (BZ_MSM_BA=1): workspace-bound, left alone
+  int want = -1, rounds = -1;
+  if (const char* e = getenv("BZ_MSM_BA2")) want = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("BZ_MSM_BA2_ROUNDS")) rounds = atoi(e);
+  if (m->acc_mode >= 0) want = m->acc_mode == 2 ? 1 : 0;
+  if (m->acc_rounds >= 0) rounds = m->acc_rounds;
+  const uint32_t L = p.seg_len;
+  const uint64_t total = (uint64_t)p.W * p.Ms;
+  const double avg = (double)total / ((double)p.W * (double)p.nb);   // entries per bucket (upper bound: zero digits drop out)
+  const bool on = want >= 0 ? want != 0 : (BZ_MSM_BA2_DEFAULT && avg >= 16.0 && L >= 64);
+  p.batch_affine = 0;
+  if (!on) return BZ_OK;
+  // tree rounds: while the runs still hold pairs (avg / 2^r >= 2) and a round still offers >= 16 additions per thread
+  int r = 0;
+  while (r < 6 && avg / (double)(1u << r) >= 2.0 && (double)L / (double)(2u << r) >= 16.0) r++;
+  r = std::max(1, r);
+  if (rounds >= 0) r = std::min(rounds, 8);
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->dc->device);
+  const uint64_t want_ctas = (uint64_t)sms * BZ_BA2_CTAS_PER_SM;
+  p.ba_rounds = r;
+  p.ba_cap = L / 2 + 32;
+  p.ba_ctas = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(want_ctas, (p.nseg + 127) / 128));
+  // three arrays (x, y, running products) of ba_cap slots per lane, one set per resident warp
+  const size_t bytes = (size_t)3 * p.ba_cap * m->ops->fq_bytes * 32 * p.ba_ctas * 4;
+  if (m->ba2_cap < bytes) {
+    if (m->ba2_scratch) cudaFree(m->ba2_scratch);   // waits for outstanding work
+    m->ba2_scratch = nullptr;
+    m->ba2_cap = 0;
+    if (cudaMalloc(&m->ba2_scratch, bytes) != cudaSuccess) {
+      cudaGetLastError();
+      return BZ_OK;   // no room for the scratch: the XYZZ sweep needs none
+    }
+    m->ba2_cap = bytes;
+  }
+  m->ws.ba2_scratch = m->ba2_scratch;
+  p.batch_affine = 2;
+  return BZ_OK;
+}
+
 // enqueue the whole pipeline for one task on the client's stream
 static int32_t launch_task(bz_msm* m) {
   bz_dclient* dc = m->dc;
@@ -487,6 +510,8 @@ static int32_t launch_task(bz_msm* m) {
     rc = make_plan(m, M, wps, false);
     if (rc) return rc;
   }
+  rc = plan_accumulate(m);
+  if (rc) return rc;
   const size_t rs = 3 * (size_t)m->ops->fq_bytes;
   const bool ranked = dc->comm != nullptr && dc->world > 1;
   if (ranked) { rc = leaf_comb_reserve(m, rs * (dc->world + 1)); if (rc) return rc; }

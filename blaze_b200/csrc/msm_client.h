@@ -71,6 +71,8 @@ struct bz_msm {
   uint64_t table_uses = 0;       // MSMs launched on the current arena table
   uint8_t* comb_dev = nullptr;   // scratch of the result combine (ranked / group / bz_msm_combine_results)
   size_t comb_cap = 0;
+  void* ba2_scratch = nullptr;   // per-warp scratch of the batched-affine sweep (allocated on first use)
+  size_t ba2_cap = 0;
   uint8_t* dma_points = nullptr;
   size_t dma_points_cap = 0;
   // DMA mode: the points travel on the copy stream BEHIND the scalars, so digits + sort of the task run while

@@ -67,7 +67,6 @@ struct MsmPlan {
   int ba_rounds;           // batch_affine == 2: tree rounds per segment before the XYZZ fold
   uint32_t ba_cap;         //                    scratch slots per lane
   uint32_t ba_ctas;        //                    persistent grid size
-  int acc_mode_req, acc_rounds_req;   // what the client asked for when the plan was made (-1 = automatic)
   uint32_t chunk;          // entries per reduce thread at every level of the running-sum recursion (power of two)
   uint32_t nchunks;        // ceil(nb / chunk): level-0 chunk count
   DigitConst dc;
