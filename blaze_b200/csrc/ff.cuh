@@ -707,8 +707,18 @@ struct ff {
     return mul(mul(y, r2), r2);
   }
 
-  // a^(p-2): only used once per MSM (result normalisation) and in input generators
+  // a^-1 (0 -> 0).  Division steps (inv_gcd) everywhere: the window-table build, the result normalisation of every
+  // task and the multi-GPU combine all sit on latency-critical single-thread paths where the Fermat ladder's ~1.5 * 32 N
+  // dependent field products cost ~0.5 ms.
   BZ_HDI static E inv(const E& a) {
+#if defined(__CUDACC__)
+    return inv_gcd_call(a);
+#else
+    return inv_gcd(a);
+#endif
+  }
+  // a^(p-2): the textbook inverse, kept as the independent check of inv_gcd (tests/test_device_math_on_host.py)
+  BZ_HDI static E inv_fermat(const E& a) {
     uint32_t e[N];
     // e = p - 2   (p odd and > 2, so only limb 0 changes... unless limb 0 < 2)
     e[0] = cc::sub_cc(F::mod()[0], 2u);

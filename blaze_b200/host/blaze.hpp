@@ -55,6 +55,14 @@ class DriverClient {
   void reset_sensor_data() { check(bz_dclient_reset_sensor_data(h_)); }
   void setup_before_load_binary() { check(bz_dclient_setup_before_load_binary(h_)); }
   uint32_t load_binary(const std::vector<uint8_t>& b) { check(bz_dclient_load_binary(h_, b.data(), b.size())); return 0; }
+  // ---- multi-GPU (B200 additions).  `id` may be a device list ("0,1,2,3"): one client over several GPUs.
+  uint32_t device_count() { uint32_t n; check(bz_dclient_device_count(h_, &n)); return n; }
+  // one process per GPU: make the 128-byte id on one rank, hand it to all ranks, then comm_init on each
+  static std::vector<uint8_t> comm_unique_id() { std::vector<uint8_t> v(128); check(bz_comm_unique_id(v.data())); return v; }
+  void comm_init(int rank, int world, const std::vector<uint8_t>& unique_id) {
+    if (unique_id.size() != 128) throw DriverClientError(DriverClientError::InvalidPrimitiveParam, "unique id must be 128 bytes");
+    check(bz_dclient_comm_init(h_, rank, world, unique_id.data()));
+  }
   bz_dclient* raw() const { return h_; }
   DriverConfig cfg;
 
@@ -106,7 +114,14 @@ class MSMClient {   // impl DriverPrimitive<MSMInit, MSMParams, MSMInput, MSMRes
     check(bz_msm_get_data_from_hbm(h_, v.data(), len, addr, off));
     return v;
   }
+  // get_api(), msm_api.rs:324-330: the register file (msm_hw_code.rs:6-55), word index = offset / 4
+  std::vector<uint32_t> get_api() { std::vector<uint32_t> v(82); check(bz_msm_get_api(h_, v.data(), v.size())); return v; }
   // ---- B200 additions (all optional)
+  float table_build_ms() { float v; check(bz_msm_table_build_ms(h_, &v)); return v; }
+  // -1 automatic / 0 XYZZ sweep / 2 fused batched-affine sweep
+  void set_accumulate_mode(int mode, int rounds = -1) { check(bz_msm_set_accumulate_mode(h_, mode, rounds)); }
+  // n factor-1 bases at src -> the reference's x8 precomputed records at dst, derived on the device
+  void expand_precompute(uint64_t src_addr, uint64_t n, uint64_t dst_addr) { check(bz_msm_expand_precompute(h_, src_addr, n, dst_addr)); }
   struct PhaseTimes { float total, sort, accumulate, reduce; };
   PhaseTimes phase_times() { float v[4]; check(bz_msm_phase_times(h_, v)); return {v[0], v[1], v[2], v[3]}; }
   struct PlanInfo { uint32_t c, windows, buckets_per_set, segment, bucket_sets; bool merged_table; uint32_t merged_table_mib; };
@@ -222,6 +237,13 @@ class PoseidonClient {   // impl DriverPrimitive<Hash, PoseidonInitializeParamet
   uint32_t get_num_of_pending_results() { uint32_t v; check(bz_poseidon_get_num_of_pending_results(h_, &v)); return v; }
   std::vector<uint8_t> get_raw_results(uint32_t n) { std::vector<uint8_t> v((size_t)n * 64); check(bz_poseidon_get_raw_results(h_, n, v.data())); return v; }
   uint32_t get_last_hash_sent_to_host() { uint32_t v; check(bz_poseidon_get_last_hash_sent_to_host(h_, &v)); return v; }
+  // ---- B200 additions
+  float device_ms() { float v; check(bz_poseidon_device_ms(h_, &v)); return v; }
+  std::vector<uint8_t> permute(const std::vector<uint8_t>& states, int t, int mds_mode = 0) {   // bare permutation (KATs)
+    std::vector<uint8_t> out(states.size());
+    check(bz_poseidon_permute(h_, t, mds_mode, states.data(), states.size() / (32 * (size_t)t), out.data()));
+    return out;
+  }
   DriverClient dclient;   // pub field `dclient` in the reference (poseidon_api.rs:15-17)
 
  private:

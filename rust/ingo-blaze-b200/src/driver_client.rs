@@ -32,12 +32,22 @@ unsafe impl Send for DriverClient {}
 unsafe impl Sync for DriverClient {}
 
 impl DriverClient {
-    /// `id` = the slot string of the reference = CUDA device ordinal (`dclient.rs:79-86`).
+    /// `id` = the slot string of the reference = CUDA device ordinal (`dclient.rs:79-86`); a comma-separated list
+    /// ("0,1,2,3,4,5,6,7") opens ONE client over several GPUs: an `MSMClient` built on it shards bases and scalars over
+    /// them and still returns one `MSMResult` per task.
     pub fn new(id: &str, cfg: DriverConfig) -> Self {
         let mut h = std::ptr::null_mut();
         let cid = CString::new(id).unwrap();
         check(unsafe { ffi::bz_dclient_new(cid.as_ptr(), cfg.card_type, &mut h) }).unwrap(); // the reference unwrap()s the open too
         DriverClient { h, cfg }
+    }
+    /// Number of GPUs behind this client.
+    pub fn device_count(&self) -> Result<u32> { let mut n = 0; check(unsafe { ffi::bz_dclient_device_count(self.h, &mut n) }).map(|_| n) }
+    /// One process per GPU: 128-byte NCCL id, made on one rank and handed to all of them.
+    pub fn comm_unique_id() -> Result<[u8; 128]> { let mut id = [0u8; 128]; check(unsafe { ffi::bz_comm_unique_id(id.as_mut_ptr()) }).map(|_| id) }
+    /// One process per GPU: this client becomes rank `rank` of `world`; MSM results are summed over the ranks on the device.
+    pub fn comm_init(&self, rank: i32, world: i32, unique_id: &[u8; 128]) -> Result<()> {
+        check(unsafe { ffi::bz_dclient_comm_init(self.h, rank, world, unique_id.as_ptr()) })
     }
     pub fn reset(&self) -> Result<()> { check(unsafe { ffi::bz_dclient_reset(self.h) }) }
     pub fn dma_write(&self, base_address: u64, offset: u64, data: &[u8]) -> Result<()> {

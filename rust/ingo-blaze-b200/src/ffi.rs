@@ -20,6 +20,9 @@ extern "C" {
     pub fn bz_dclient_reset_sensor_data(dc: *mut bz_dclient) -> i32;
     pub fn bz_dclient_setup_before_load_binary(dc: *mut bz_dclient) -> i32;
     pub fn bz_dclient_load_binary(dc: *mut bz_dclient, image: *const u8, len: usize) -> i32;
+    pub fn bz_dclient_device_count(dc: *mut bz_dclient, n: *mut u32) -> i32;
+    pub fn bz_comm_unique_id(out: *mut u8) -> i32;
+    pub fn bz_dclient_comm_init(dc: *mut bz_dclient, rank: i32, world: i32, unique_id: *const u8) -> i32;
 
     pub fn bz_msm_new(dc: *mut bz_dclient, curve: i32, mem_type: i32, is_precompute: i32, out: *mut *mut bz_msm) -> i32;
     pub fn bz_msm_free(m: *mut bz_msm) -> i32;
@@ -37,6 +40,7 @@ extern "C" {
     pub fn bz_msm_get_data_from_hbm(m: *mut bz_msm, out: *mut u8, len: usize, addr: u64, offset: u64) -> i32;
     pub fn bz_msm_sizes(m: *mut bz_msm, scalar: *mut u32, point: *mut u32, result: *mut u32, factor: *mut u32) -> i32;
     pub fn bz_msm_set_precompute(m: *mut bz_msm, mode: i32) -> i32;
+    pub fn bz_msm_get_api(m: *mut bz_msm, regs: *mut u32, n_words: usize) -> i32;
 
     pub fn bz_ntt_new(dc: *mut bz_dclient, ntt_type: i32, out: *mut *mut bz_ntt) -> i32;
     pub fn bz_ntt_free(t: *mut bz_ntt) -> i32;

@@ -70,6 +70,13 @@ impl MSMClient {
     /// B200 addition: 0 = never, 1 = on reuse (default), 2 = always derive the table of window multiples
     /// (2^(c w) P) from an HBM-resident point set so that all windows share one bucket set.
     pub fn set_precompute(&self, mode: i32) -> Result<()> { check(unsafe { ffi::bz_msm_set_precompute(self.h, mode) }) }
-    pub fn get_api(&self) {}
+    /// `msm_api.rs:324-330`: reads every `INGO_MSM_ADDR` register (word index = offset / 4, `msm_hw_code.rs:6-55`);
+    /// the reference discards the values, so does this -- `get_api_values` returns them.
+    pub fn get_api(&self) { let _ = self.get_api_values(); }
+    pub fn get_api_values(&self) -> Result<Vec<u32>> {
+        let mut regs = vec![0u32; 82];
+        check(unsafe { ffi::bz_msm_get_api(self.h, regs.as_mut_ptr(), regs.len()) })?;
+        Ok(regs)
+    }
 }
 impl Drop for MSMClient { fn drop(&mut self) { unsafe { ffi::bz_msm_free(self.h); } } }

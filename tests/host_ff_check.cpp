@@ -36,6 +36,7 @@ static int field_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, in
     case 7: r = ff<F>::mul_sub2(x, y, ff<F>::add(x, y), ff<F>::sub(x, y)); break;   // xy - (x+y)(x-y)
     case 8: r = ff<F>::mul2(x, y, ff<F>::add(x, y), ff<F>::sub(x, y)); break;
     case 11: r = ff<F>::inv_gcd(x); break;   // division-step inverse
+    case 12: r = ff<F>::inv_fermat(x); break;
     case 9: r = ff<F>::mul_kara(x, y); break;   // Karatsuba product + reduction-only Montgomery
     case 10:
       if constexpr (F::BITS + 2 <= 32 * F::N) r = ff<F>::mul2_kara(x, y, ff<F>::add(x, y), ff<F>::sub(x, y));

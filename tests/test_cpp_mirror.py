@@ -36,4 +36,4 @@ def test_cpp_mirror_compiles_and_fails_loudly_without_a_device(exe):
 def test_cpp_integration_tests(exe):
     env = dict(os.environ, MSM_SIZE="8192", ID="0")
     r = subprocess.run([exe], capture_output=True, text=True, env=env, timeout=900)
-    assert r.returncode == 0 and "8 passed" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.returncode == 0 and "9 passed" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

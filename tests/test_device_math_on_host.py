@@ -47,6 +47,10 @@ def test_field_ops(hc, name):
             assert fop(hc, fid, 10, a, b, nb) == (a * b + (a + b) * (a - b)) % p
         for a in vals[1:10]:
             assert fop(hc, fid, 4, a, 0, nb) == pow(a, -1, p)
+            assert fop(hc, fid, 12, a, 0, nb) == pow(a, -1, p)                        # Fermat ladder
+        for a in vals[1:]:
+            assert fop(hc, fid, 11, a, 0, nb) == pow(a, -1, p)                        # division steps (what inv() uses)
+        assert fop(hc, fid, 11, 0, 0, nb) == 0 and fop(hc, fid, 4, 0, 0, nb) == 0
 
 
 @pytest.mark.parametrize("name", ["BLS12_381", "BLS12_377", "BN254"])
