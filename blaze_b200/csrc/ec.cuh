@@ -132,6 +132,51 @@ struct ec {
     acc.Y = Y3;
   }
 
+#ifdef __CUDACC__
+  // ---- acc += b by FOUR lanes (an aligned quad of a warp, all holding the same acc and b).  The 14 field products
+  // of the XYZZ addition form four dependency levels of <= 4 independent products: every lane computes one product of
+  // the level and the quad exchanges the results with shuffles, so the latency of an addition is ~4 product latencies
+  // instead of 14.  For the latency-bound tails of the pipeline (upper levels of the bucket reduction and of the
+  // partial-merge tree: a few thousand additions on chains that one thread walks serially), not for throughput.
+  __device__ __forceinline__ static E quad_get(const E& v, int src, unsigned mask) {
+    E r;
+#pragma unroll
+    for (int i = 0; i < Fq::N; i++) r.v[i] = __shfl_sync(mask, v.v[i], src, 4);
+    return r;
+  }
+  __device__ __forceinline__ static E sel4(int q, const E& a, const E& b, const E& c, const E& d) {
+    E r;
+#pragma unroll
+    for (int i = 0; i < Fq::N; i++) r.v[i] = q == 0 ? a.v[i] : (q == 1 ? b.v[i] : (q == 2 ? c.v[i] : d.v[i]));
+    return r;
+  }
+  __device__ static void add_quad(P& acc, const P& b) {
+    const int lane = threadIdx.x & 31, q = lane & 3;
+    const unsigned mask = 0xFu << (lane & ~3);
+    if (is_inf(b)) return;                    // uniform within the quad: all four lanes hold the same values
+    if (is_inf(acc)) { acc = b; return; }
+    const E m1 = F::mul(sel4(q, acc.X, b.X, acc.Y, b.Y), sel4(q, b.ZZ, acc.ZZ, b.ZZZ, acc.ZZZ));
+    const E U1 = quad_get(m1, 0, mask), U2 = quad_get(m1, 1, mask), S1 = quad_get(m1, 2, mask), S2 = quad_get(m1, 3, mask);
+    const E Pd = F::sub(U2, U1), Rd = F::sub(S2, S1);
+    if (F::is_zero(Pd)) {
+      if (F::is_zero(Rd)) acc = dbl(acc);
+      else acc = infinity();
+      return;
+    }
+    const E m2 = F::mul(sel4(q, Pd, Rd, acc.ZZ, acc.ZZZ), sel4(q, Pd, Rd, b.ZZ, b.ZZZ));
+    const E PP = quad_get(m2, 0, mask), RR = quad_get(m2, 1, mask), ZZ12 = quad_get(m2, 2, mask), ZZZ12 = quad_get(m2, 3, mask);
+    const E m3 = F::mul(sel4(q, Pd, U1, ZZ12, ZZ12), PP);
+    const E PPP = quad_get(m3, 0, mask), Q = quad_get(m3, 1, mask), ZZ3 = quad_get(m3, 2, mask);
+    const E X3 = F::sub(F::sub(RR, PPP), F::dbl(Q));
+    const E m4 = F::mul(sel4(q, Rd, S1, ZZZ12, ZZZ12), sel4(q, F::sub(Q, X3), PPP, PPP, PPP));
+    const E t1 = quad_get(m4, 0, mask), t2 = quad_get(m4, 1, mask), ZZZ3 = quad_get(m4, 2, mask);
+    acc.X = X3;
+    acc.Y = F::sub(t1, t2);
+    acc.ZZ = ZZ3;
+    acc.ZZZ = ZZZ3;
+  }
+#endif
+
   // ---- affine + affine with a shared ("batched") inversion --------------------------------------
   // ba_classify picks the denominator whose inverse the addition needs and says which formula applies;
   // ba_finish completes the addition given that inverse.  Denominators are never zero, so thousands of

@@ -440,7 +440,9 @@ k_accumulate_tma(const AffineT<C>* __restrict__ table, const uint32_t* __restric
 // array; it walks the children's (head, tail) partial entries in order, sums equal ids, and flushes
 // a finished run to its bucket if the bucket lies inside the span, else to its own head / tail slot.
 // The top level spans everything, so every remaining run lands in its bucket.
-template <class C>
+// QUAD: four lanes per group (ec<C>::add_quad): the same walk with ~3.5x shorter addition latency, for the levels that
+// are too small to fill the machine (every level but the first of a large MSM)
+template <class C, bool QUAD>
 __global__ void __launch_bounds__(128) k_merge_level(const uint32_t* __restrict__ goff, uint32_t ngoff,
                                                      XyzzM<C>* __restrict__ buckets,
                                                      const uint32_t* __restrict__ in_id,
@@ -451,7 +453,9 @@ __global__ void __launch_bounds__(128) k_merge_level(const uint32_t* __restrict_
   typedef dev<C> D;
   typedef ec<C> G;
   uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= n_groups) return;
+  const bool writer = !QUAD || (threadIdx.x & 3) == 0;
+  if (QUAD) g >>= 2;
+  if (g >= n_groups) return;   // whole quads leave together (n_groups * 4 threads are launched in multiples of 4)
   const uint64_t total = __ldg(goff + ngoff);
   const uint64_t lo = g * span;
   uint64_t hi = lo + span;
@@ -467,20 +471,23 @@ __global__ void __launch_bounds__(128) k_merge_level(const uint32_t* __restrict_
     if (id != cur) {
       if (cur != 0xffffffffu) {
         bool left_open = (uint64_t)goff[cur] < lo, right_open = (uint64_t)goff[cur + 1] > hi;
-        if (!left_open && !right_open) D::store_xyzz(buckets + cur, acc);
-        else if (left_open) { id0 = cur; D::store_xyzz(out_pt + 2 * g, acc); }
-        else { id1 = cur; D::store_xyzz(out_pt + 2 * g + 1, acc); }
+        if (!left_open && !right_open) { if (writer) D::store_xyzz(buckets + cur, acc); }
+        else if (left_open) { id0 = cur; if (writer) D::store_xyzz(out_pt + 2 * g, acc); }
+        else { id1 = cur; if (writer) D::store_xyzz(out_pt + 2 * g + 1, acc); }
       }
       if (id == 0xfffffffeu) break;
       cur = id;
       acc = D::load_xyzz(in_pt + e);
     } else {
       XYZZ<C> o = D::load_xyzz(in_pt + e);
-      G::add(acc, o);
+      if (QUAD) G::add_quad(acc, o);
+      else G::add(acc, o);
     }
   }
-  out_id[2 * g] = id0;
-  out_id[2 * g + 1] = id1;
+  if (writer) {
+    out_id[2 * g] = id0;
+    out_id[2 * g + 1] = id1;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -493,7 +500,7 @@ __global__ void __launch_bounds__(128) k_merge_level(const uint32_t* __restrict_
 // doublings per thread), so the weighted sums R need no rescaling, and the level results are folded as they go:
 //     V^l_k = R^l_k + sum_{j in chunk k} V^{l-1}_j
 // so the window total is the single V of the top level.
-template <class C>
+template <class C, bool QUAD>
 __global__ void __launch_bounds__(128, 2)
 k_reduce_level(const XyzzM<C>* __restrict__ A, const XyzzM<C>* __restrict__ Vin, uint32_t n, uint32_t a_stride,
                int cbits /* >= 0: entry i lives in slot (i & (2^cbits - 1)) * nfine + (i >> cbits) */, uint32_t nfine,
@@ -503,6 +510,8 @@ k_reduce_level(const XyzzM<C>* __restrict__ A, const XyzzM<C>* __restrict__ Vin,
   typedef dev<C> D;
   typedef ec<C> G;
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool writer = !QUAD || (threadIdx.x & 3) == 0;
+  if (QUAD) t >>= 2;   // four lanes per chunk (ec<C>::add_quad): the latency-bound upper levels
   if (t >= (uint32_t)W * nchunks) return;
   uint32_t w = t / nchunks, k = t % nchunks;
   const XyzzM<C>* a = A + (uint64_t)w * a_stride;
@@ -510,27 +519,28 @@ k_reduce_level(const XyzzM<C>* __restrict__ A, const XyzzM<C>* __restrict__ Vin,
   auto slot = [&](uint32_t i) { return cbits >= 0 ? (i & cmask) * nfine + (i >> cbits) : i; };
   uint32_t lo = k * s, hi = lo + s;
   if (hi > n) hi = n;
+  auto plus = [&](XYZZ<C>& x, const XYZZ<C>& y) { if (QUAD) G::add_quad(x, y); else G::add(x, y); };
   XYZZ<C> S = G::infinity(), R = G::infinity();
   for (uint32_t i = hi - 1; i > lo; i--) {
     XYZZ<C> v = D::load_xyzz(a + slot(i));
-    G::add(S, v);
-    G::add(R, S);
+    plus(S, v);
+    plus(R, S);
   }
   {
     XYZZ<C> v = D::load_xyzz(a + slot(lo));
-    G::add(S, v);
+    plus(S, v);
   }
-  if (first) G::add(R, S);
+  if (first) plus(R, S);
   if (Vin) {
     const XyzzM<C>* vin = Vin + (uint64_t)w * n;
     for (uint32_t i = lo; i < hi; i++) {
       XYZZ<C> v = D::load_xyzz(vin + i);
-      G::add(R, v);
+      plus(R, v);
     }
   }
-  D::store_xyzz(Vout + t, R);
+  if (writer) D::store_xyzz(Vout + t, R);
   for (int d = 0; d < out_shift; d++) S = G::dbl(S);
-  D::store_xyzz(Sout + t, S);
+  if (writer) D::store_xyzz(Sout + t, S);
 }
 
 // Horner over the window sums, normalise, serialise
@@ -674,9 +684,12 @@ struct CurveLaunch {
         const uint32_t group = merge_group(level, p.nseg);
         const uint64_t span = child_span * group;   // sorted positions covered by one group
         uint64_t n_groups = (n_children + group - 1) / group;
-        k_merge_level<C><<<(unsigned)((n_groups + 127) / 128), 128, 0, st>>>(ws.goff, ngoff, buckets, in_id, in_pt,
-                                                                             n_children, group, span, out_id, out_pt,
-                                                                             n_groups);
+        if (n_groups <= 16384)   // too few walks to fill the machine: four lanes per walk
+          k_merge_level<C, true><<<(unsigned)((4 * n_groups + 127) / 128), 128, 0, st>>>(ws.goff, ngoff, buckets, in_id, in_pt, n_children,
+                                                                                         group, span, out_id, out_pt, n_groups);
+        else
+          k_merge_level<C, false><<<(unsigned)((n_groups + 127) / 128), 128, 0, st>>>(ws.goff, ngoff, buckets, in_id, in_pt, n_children,
+                                                                                      group, span, out_id, out_pt, n_groups);
         g_kernel_launches += 1;
         if (n_groups == 1) break;
         in_id = out_id;
@@ -707,8 +720,13 @@ struct CurveLaunch {
       XyzzM<C>* Sout = scratch[level & 1];
       XyzzM<C>* Vout = Sout + (size_t)p.W * nch;
       uint32_t nt = (uint32_t)p.W * nch;
-      k_reduce_level<C><<<(nt + 127) / 128, 128, 0, st>>>(A, Vin, n, a_stride, perm_bits, 1u << p.fb, s, nch, p.W,
-                                                        level == 0 ? 1 : 0, nch == 1 ? 0 : log_s, Sout, Vout);
+      if (nt <= 8192)   // latency-bound level: four lanes per chunk (measured at 2^21 buckets: 32768 chunks are still
+                        // throughput-bound -- 0.22 ms with one thread per chunk, 0.54 ms with four)
+        k_reduce_level<C, true><<<(4 * nt + 127) / 128, 128, 0, st>>>(A, Vin, n, a_stride, perm_bits, 1u << p.fb, s, nch, p.W,
+                                                                      level == 0 ? 1 : 0, nch == 1 ? 0 : log_s, Sout, Vout);
+      else
+        k_reduce_level<C, false><<<(nt + 127) / 128, 128, 0, st>>>(A, Vin, n, a_stride, perm_bits, 1u << p.fb, s, nch, p.W,
+                                                                   level == 0 ? 1 : 0, nch == 1 ? 0 : log_s, Sout, Vout);
       g_kernel_launches += 1;
       top = Vout;
       if (nch == 1) break;
