@@ -492,7 +492,21 @@ extern "C" int32_t bz_poseidon_set_data(bz_poseidon* p, const uint8_t* input, si
       p->elems_tree++;
     } else {   // bulk: as many whole elements as the current tree still takes
       const size_t take = (size_t)std::min<uint64_t>(n_el - e, p->d_inputs_cap - p->elems_tree);
-      p->staged.insert(p->staged.end(), input + e * 32, input + (e + take) * 32);
+      if (take >= 4096) {
+        // large burst: straight from the caller's buffer to the device, behind whatever single elements are staged
+        cudaStream_t st = dc_stream(p->dc);
+        if (!p->staged.empty()) {
+          CUDA_TRY(BZ_ERR_WRITE, cudaMemcpyAsync(p->d_inputs + p->elems_on_device * 32, p->staged.data(), p->staged.size(), cudaMemcpyHostToDevice, st));
+          CUDA_TRY(BZ_ERR_WRITE, cudaStreamSynchronize(st));
+          p->elems_on_device += p->staged.size() / 32;
+          p->staged.clear();
+        }
+        CUDA_TRY(BZ_ERR_WRITE, cudaMemcpyAsync(p->d_inputs + p->elems_on_device * 32, input + e * 32, take * 32, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(BZ_ERR_WRITE, cudaStreamSynchronize(st));   // the caller may reuse `input` on return
+        p->elems_on_device += take;
+      } else {
+        p->staged.insert(p->staged.end(), input + e * 32, input + (e + take) * 32);
+      }
       e += take;
       p->elems_total += take;
       p->elems_tree += take;
