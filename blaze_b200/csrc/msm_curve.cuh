@@ -443,20 +443,11 @@ k_accumulate_tma(const AffineT<C>* __restrict__ table, const uint32_t* __restric
 // QUAD: four lanes per group (ec<C>::add_quad): the same walk with ~3.5x shorter addition latency, for the levels that
 // are too small to fill the machine (every level but the first of a large MSM)
 template <class C, bool QUAD>
-__global__ void __launch_bounds__(128) k_merge_level(const uint32_t* __restrict__ goff, uint32_t ngoff,
-                                                     XyzzM<C>* __restrict__ buckets,
-                                                     const uint32_t* __restrict__ in_id,
-                                                     const XyzzM<C>* __restrict__ in_pt, uint64_t n_children,
-                                                     uint32_t group, uint64_t span /* positions per group */,
-                                                     uint32_t* __restrict__ out_id, XyzzM<C>* __restrict__ out_pt,
-                                                     uint64_t n_groups) {
+__device__ __forceinline__ void merge_walk(uint64_t g, bool writer, const uint32_t* goff, uint64_t total, XyzzM<C>* buckets,
+                                           const uint32_t* in_id, const XyzzM<C>* in_pt, uint64_t n_children, uint32_t group,
+                                           uint64_t span, uint32_t* out_id, XyzzM<C>* out_pt, uint64_t n_groups) {
   typedef dev<C> D;
   typedef ec<C> G;
-  uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool writer = !QUAD || (threadIdx.x & 3) == 0;
-  if (QUAD) g >>= 2;
-  if (g >= n_groups) return;   // whole quads leave together (n_groups * 4 threads are launched in multiples of 4)
-  const uint64_t total = __ldg(goff + ngoff);
   const uint64_t lo = g * span;
   uint64_t hi = lo + span;
   if (hi > total || n_groups == 1) hi = total;
@@ -490,6 +481,47 @@ __global__ void __launch_bounds__(128) k_merge_level(const uint32_t* __restrict_
   }
 }
 
+template <class C, bool QUAD>
+__global__ void __launch_bounds__(128) k_merge_level(const uint32_t* __restrict__ goff, uint32_t ngoff,
+                                                     XyzzM<C>* __restrict__ buckets,
+                                                     const uint32_t* __restrict__ in_id,
+                                                     const XyzzM<C>* __restrict__ in_pt, uint64_t n_children,
+                                                     uint32_t group, uint64_t span /* positions per group */,
+                                                     uint32_t* __restrict__ out_id, XyzzM<C>* __restrict__ out_pt,
+                                                     uint64_t n_groups) {
+  uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool writer = !QUAD || (threadIdx.x & 3) == 0;
+  if (QUAD) g >>= 2;
+  if (g >= n_groups) return;   // whole quads leave together (n_groups * 4 threads are launched in multiples of 4)
+  merge_walk<C, QUAD>(g, writer, goff, __ldg(goff + ngoff), buckets, in_id, in_pt, n_children, group, span, out_id, out_pt, n_groups);
+}
+
+// ALL remaining levels of the merge tree in one launch (one CTA, four lanes per walk, __syncthreads between levels): from
+// the level with <= 64 groups on, every level is a one-CTA launch with a ~45 us floor of its own otherwise
+template <class C>
+__global__ void __launch_bounds__(256, 1)
+k_merge_top(const uint32_t* goff, uint32_t ngoff, XyzzM<C>* buckets, const uint32_t* in_id, const XyzzM<C>* in_pt, uint64_t n_children,
+            uint32_t group, uint64_t child_span, uint32_t* out_id, XyzzM<C>* out_pt) {
+  const uint32_t quad = threadIdx.x >> 2, nquads = blockDim.x >> 2;
+  const bool writer = (threadIdx.x & 3) == 0;
+  const uint64_t total = goff[ngoff];
+  for (;;) {
+    const uint64_t span = child_span * group;
+    const uint64_t n_groups = (n_children + group - 1) / group;
+    for (uint64_t g = quad; g < n_groups; g += nquads)
+      merge_walk<C, true>(g, writer, goff, total, buckets, in_id, in_pt, n_children, group, span, out_id, out_pt, n_groups);
+    __syncthreads();
+    if (n_groups == 1) break;
+    in_id = out_id;
+    in_pt = out_pt;
+    out_id += 2 * n_groups;
+    out_pt += 2 * n_groups;
+    n_children = n_groups;
+    child_span = span;
+    group = MERGE_GROUP_UPPER;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // bucket reduction.  Slot i of the bucket array holds the bucket of VALUE i + 1 (zero digits never reach the
 // sort), so per window we need T = sum_i (i+1) A[i].  Chunks of s entries:
@@ -500,19 +532,15 @@ __global__ void __launch_bounds__(128) k_merge_level(const uint32_t* __restrict_
 // doublings per thread), so the weighted sums R need no rescaling, and the level results are folded as they go:
 //     V^l_k = R^l_k + sum_{j in chunk k} V^{l-1}_j
 // so the window total is the single V of the top level.
+// one chunk of one level (see above); t = chunk index over all windows.  QUAD: executed by an aligned quad of lanes
+// (ec<C>::add_quad), the stores by its first lane
 template <class C, bool QUAD>
-__global__ void __launch_bounds__(128, 2)
-k_reduce_level(const XyzzM<C>* __restrict__ A, const XyzzM<C>* __restrict__ Vin, uint32_t n, uint32_t a_stride,
-               int cbits /* >= 0: entry i lives in slot (i & (2^cbits - 1)) * nfine + (i >> cbits) */, uint32_t nfine,
-               uint32_t s, uint32_t nchunks, int W, int first /* level 0: weights t+1 instead of t */,
-               int out_shift /* log2(s), 0 at the top level: Sout = 2^out_shift * chunk sum */,
-               XyzzM<C>* __restrict__ Sout, XyzzM<C>* __restrict__ Vout) {
+__device__ __forceinline__ void reduce_chunk(uint32_t t, bool writer, const XyzzM<C>* A, const XyzzM<C>* Vin,   // no __restrict__: the
+                                             uint32_t n, uint32_t a_stride, int cbits, uint32_t nfine, uint32_t s,   // fused kernel reads what
+                                             uint32_t nchunks, int first, int out_shift, XyzzM<C>* Sout,           // its previous level wrote
+                                             XyzzM<C>* Vout) {
   typedef dev<C> D;
   typedef ec<C> G;
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool writer = !QUAD || (threadIdx.x & 3) == 0;
-  if (QUAD) t >>= 2;   // four lanes per chunk (ec<C>::add_quad): the latency-bound upper levels
-  if (t >= (uint32_t)W * nchunks) return;
   uint32_t w = t / nchunks, k = t % nchunks;
   const XyzzM<C>* a = A + (uint64_t)w * a_stride;
   const uint32_t cmask = cbits >= 0 ? (1u << cbits) - 1 : 0;
@@ -543,12 +571,62 @@ k_reduce_level(const XyzzM<C>* __restrict__ A, const XyzzM<C>* __restrict__ Vin,
   if (writer) D::store_xyzz(Sout + t, S);
 }
 
+template <class C, bool QUAD>
+__global__ void __launch_bounds__(128, 2)
+k_reduce_level(const XyzzM<C>* __restrict__ A, const XyzzM<C>* __restrict__ Vin, uint32_t n, uint32_t a_stride,
+               int cbits /* >= 0: entry i lives in slot (i & (2^cbits - 1)) * nfine + (i >> cbits) */, uint32_t nfine,
+               uint32_t s, uint32_t nchunks, int W, int first /* level 0: weights t+1 instead of t */,
+               int out_shift /* log2(s), 0 at the top level: Sout = 2^out_shift * chunk sum */,
+               XyzzM<C>* __restrict__ Sout, XyzzM<C>* __restrict__ Vout) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool writer = !QUAD || (threadIdx.x & 3) == 0;
+  if (QUAD) t >>= 2;   // four lanes per chunk (ec<C>::add_quad): the latency-bound upper levels
+  if (t >= (uint32_t)W * nchunks) return;
+  reduce_chunk<C, QUAD>(t, writer, A, Vin, n, a_stride, cbits, nfine, s, nchunks, first, out_shift, Sout, Vout);
+}
+
+template <class C>
+__device__ void finish_windows(const XyzzM<C>* win, int W, int c, int raw, uint8_t* result);
+
+// ALL remaining levels of the reduction in ONE launch (one CTA, four lanes per chunk, __syncthreads between levels),
+// followed by the window combine + serialisation: used from the level whose chunk count fits the CTA.  A one-CTA launch
+// per level has a floor of ~45 us (cold instruction cache) whatever its size; at a 2^21-bucket shard this replaces six
+// launches + k_finish.
+template <class C>
+__global__ void __launch_bounds__(256, 1)
+k_reduce_top(const XyzzM<C>* A, const XyzzM<C>* Vin, uint32_t n, uint32_t a_stride, int cbits, uint32_t nfine, uint32_t s, int W, int first,
+             XyzzM<C>* buf0, XyzzM<C>* buf1, int parity, int c, int raw, uint8_t* result) {
+  const uint32_t quad = threadIdx.x >> 2, nquads = blockDim.x >> 2;
+  const bool writer = (threadIdx.x & 3) == 0;
+  const XyzzM<C>* top;
+  for (;;) {
+    int log_s = 0;
+    while ((1u << log_s) < s) log_s++;
+    const uint32_t nch = (n + s - 1) / s;
+    XyzzM<C>* Sout = parity ? buf1 : buf0;
+    XyzzM<C>* Vout = Sout + (size_t)W * nch;
+    for (uint32_t t = quad; t < (uint32_t)W * nch; t += nquads)
+      reduce_chunk<C, true>(t, writer, A, Vin, n, a_stride, cbits, nfine, s, nch, first, nch == 1 ? 0 : log_s, Sout, Vout);
+    __syncthreads();
+    top = Vout;
+    if (nch == 1) break;
+    A = Sout;
+    Vin = Vout;
+    n = nch;
+    a_stride = nch;
+    cbits = -1;
+    s = 4;
+    first = 0;
+    parity ^= 1;
+  }
+  if (threadIdx.x == 0) finish_windows<C>(top, W, c, raw, result);
+}
+
 // Horner over the window sums, normalise, serialise
 template <class C>
-__global__ void k_finish(const XyzzM<C>* __restrict__ win, int W, int c, int raw, uint8_t* __restrict__ result) {
+__device__ void finish_windows(const XyzzM<C>* win, int W, int c, int raw, uint8_t* result) {
   typedef dev<C> D;
   typedef ec<C> G;
-  if (blockIdx.x || threadIdx.x) return;
   XYZZ<C> acc = D::load_xyzz(win + (W - 1));
   for (int w = W - 2; w >= 0; w--) {
     for (int d = 0; d < c; d++) acc = G::dbl(acc);
@@ -557,6 +635,12 @@ __global__ void k_finish(const XyzzM<C>* __restrict__ win, int W, int c, int raw
   }
   if (raw) D::store_result_raw(result, acc);
   else D::store_result(result, acc);
+}
+
+template <class C>
+__global__ void k_finish(const XyzzM<C>* __restrict__ win, int W, int c, int raw, uint8_t* __restrict__ result) {
+  if (blockIdx.x || threadIdx.x) return;
+  finish_windows<C>(win, W, c, raw, result);
 }
 
 // sum n canonical result records
@@ -684,6 +768,11 @@ struct CurveLaunch {
         const uint32_t group = merge_group(level, p.nseg);
         const uint64_t span = child_span * group;   // sorted positions covered by one group
         uint64_t n_groups = (n_children + group - 1) / group;
+        if (n_groups <= 64) {   // the rest of the tree in one launch
+          k_merge_top<C><<<1, 256, 0, st>>>(ws.goff, ngoff, buckets, in_id, in_pt, n_children, group, child_span, out_id, out_pt);
+          g_kernel_launches += 1;
+          break;
+        }
         if (n_groups <= 16384)   // too few walks to fill the machine: four lanes per walk
           k_merge_level<C, true><<<(unsigned)((4 * n_groups + 127) / 128), 128, 0, st>>>(ws.goff, ngoff, buckets, in_id, in_pt, n_children,
                                                                                          group, span, out_id, out_pt, n_groups);
@@ -702,7 +791,7 @@ struct CurveLaunch {
     }
     }   // !batch_affine
     // multi-level running-sum reduction (see k_reduce_level); scratch: red_a = S / V of even levels, red_b = odd
-    g_kernel_launches += 2;   // accumulate, finish
+    g_kernel_launches += 1;   // accumulate
     // level 0 uses p.chunk entries per thread (throughput); the upper levels are tiny and latency-bound,
     // so they use chunks of 4 (total chain length ~ s log_s n is shortest for small s)
     const XyzzM<C>* A = buckets;
@@ -720,6 +809,12 @@ struct CurveLaunch {
       XyzzM<C>* Sout = scratch[level & 1];
       XyzzM<C>* Vout = Sout + (size_t)p.W * nch;
       uint32_t nt = (uint32_t)p.W * nch;
+      if (nt <= 256) {   // everything that is left fits one CTA (64 quads): all remaining levels + the window combine in one launch
+        k_reduce_top<C><<<1, 256, 0, st>>>(A, Vin, n, a_stride, perm_bits, 1u << p.fb, s, p.W, level == 0 ? 1 : 0, scratch[0], scratch[1],
+                                           level & 1, p.c, p.raw_result, ws.result);
+        g_kernel_launches += 1;
+        return;
+      }
       if (nt <= 8192)   // latency-bound level: four lanes per chunk (measured at 2^21 buckets: 32768 chunks are still
                         // throughput-bound -- 0.22 ms with one thread per chunk, 0.54 ms with four)
         k_reduce_level<C, true><<<(4 * nt + 127) / 128, 128, 0, st>>>(A, Vin, n, a_stride, perm_bits, 1u << p.fb, s, nch, p.W,
@@ -738,6 +833,7 @@ struct CurveLaunch {
       level++;
     }
     k_finish<C><<<1, 32, 0, st>>>(top, p.W, p.c, p.raw_result, ws.result);
+    g_kernel_launches += 1;
   }
   static void build_wtable(void* wtable, uint64_t n, int levels, int c, cudaStream_t st) {
     constexpr int K = 16;
