@@ -497,7 +497,7 @@ __global__ void __launch_bounds__(128) k_merge_level(const uint32_t* __restrict_
 }
 
 // ALL remaining levels of the merge tree in one launch (one CTA, four lanes per walk, __syncthreads between levels): from
-// the level with <= 64 groups on, every level is a one-CTA launch with a ~45 us floor of its own otherwise
+// the level with <= 16 groups on
 template <class C>
 __global__ void __launch_bounds__(256, 1)
 k_merge_top(const uint32_t* goff, uint32_t ngoff, XyzzM<C>* buckets, const uint32_t* in_id, const XyzzM<C>* in_pt, uint64_t n_children,
@@ -589,9 +589,7 @@ template <class C>
 __device__ void finish_windows(const XyzzM<C>* win, int W, int c, int raw, uint8_t* result);
 
 // ALL remaining levels of the reduction in ONE launch (one CTA, four lanes per chunk, __syncthreads between levels),
-// followed by the window combine + serialisation: used from the level whose chunk count fits the CTA.  A one-CTA launch
-// per level has a floor of ~45 us (cold instruction cache) whatever its size; at a 2^21-bucket shard this replaces six
-// launches + k_finish.
+// followed by the window combine + serialisation: used from the level whose chunk count fits the CTA's quads.
 template <class C>
 __global__ void __launch_bounds__(256, 1)
 k_reduce_top(const XyzzM<C>* A, const XyzzM<C>* Vin, uint32_t n, uint32_t a_stride, int cbits, uint32_t nfine, uint32_t s, int W, int first,
@@ -768,7 +766,7 @@ struct CurveLaunch {
         const uint32_t group = merge_group(level, p.nseg);
         const uint64_t span = child_span * group;   // sorted positions covered by one group
         uint64_t n_groups = (n_children + group - 1) / group;
-        if (n_groups <= 64) {   // the rest of the tree in one launch
+        if (n_groups <= 16) {   // the rest of the tree in one launch
           k_merge_top<C><<<1, 256, 0, st>>>(ws.goff, ngoff, buckets, in_id, in_pt, n_children, group, child_span, out_id, out_pt);
           g_kernel_launches += 1;
           break;
@@ -809,7 +807,9 @@ struct CurveLaunch {
       XyzzM<C>* Sout = scratch[level & 1];
       XyzzM<C>* Vout = Sout + (size_t)p.W * nch;
       uint32_t nt = (uint32_t)p.W * nch;
-      if (nt <= 256) {   // everything that is left fits one CTA (64 quads): all remaining levels + the window combine in one launch
+      if (nt <= 64) {   // one chunk per quad of one CTA: all remaining levels + the window combine in one launch (measured:
+                        // no faster than separate launches at 2^21 buckets -- the levels are chain-latency bound, ~0.12 ms
+                        // each -- but it saves the launches; with more chunks than quads it is slower)
         k_reduce_top<C><<<1, 256, 0, st>>>(A, Vin, n, a_stride, perm_bits, 1u << p.fb, s, p.W, level == 0 ? 1 : 0, scratch[0], scratch[1],
                                            level & 1, p.c, p.raw_result, ws.result);
         g_kernel_launches += 1;
