@@ -1,4 +1,4 @@
-"""One accumulate mode, a few MSMs (for ncu captures): python scripts/ba_one.py log_n mode rounds"""
+"""One accumulate mode, a few MSMs (for ncu captures): python scripts/ba_one.py log_n mode rounds [precompute_mode=2]"""
 import os
 import sys
 
@@ -16,7 +16,7 @@ dc = bz.DriverClient("0")
 p0, q = seed_points(c, 2026)
 m = bz.MSMClient.new(bz.MSMInit(bz.PointMemoryType.HBM, False, bz.Curve.BLS381), dc)
 m.generate_chain_points(p0 + q, 0, n, 0, 0)
-m.set_precompute(2)
+m.set_precompute(int(sys.argv[4]) if len(sys.argv) > 4 else 2)
 m.set_accumulate_mode(mode, rounds)
 params = bz.MSMParams(n, (0, 0))
 sc = random_scalars(c, n, seed=2027)

@@ -147,3 +147,31 @@ def test_bulk_tree_height_5_and_device_timer(dclient):
                 assert by[(l, i)] == P.hash_elems([by[(l - 1, 8 * i + j)] for j in range(8)])
     finally:
         p.close()
+
+
+def test_bulk_tree_height_6_both_kernels(dclient):
+    """32768 base-layer hashes go through the one-thread-per-hash kernel, the upper layers (4096 .. 1) through the
+    sixteen-lane kernel; sampled nodes of every layer against the oracle."""
+    h = 6
+    nbase = num_of_elements_in_base_layer(h)
+    rng = random.Random(29)
+    import numpy as np
+    raw = np.random.default_rng(31).integers(0, 256, size=(11 * nbase, 32), dtype=np.uint8)
+    raw[:, 31] &= 0x3f
+    data = raw.reshape(-1)
+    p = PoseidonClient.new(Hash.Poseidon, dclient)
+    try:
+        p.initialize(PoseidonInitializeParameters(h, TreeMode.TreeC, ""))
+        p.set_data(data)
+        n = p.get_num_of_pending_results()
+        assert n == num_of_elements_oct_tree(h)
+        res = PoseidonResult.parse_poseidon_hash_results(p.get_raw_results(n))
+        by = {(r.layer_id, r.hash_id): int.from_bytes(r.hash_byte, "little") for r in res}
+        for i in (0, 1, 12345, nbase - 1, rng.randrange(nbase)):
+            el = [int.from_bytes(bytes(data[32 * (11 * i + j):32 * (11 * i + j + 1)]), "little") for j in range(11)]
+            assert by[(0, i)] == P.hash_elems(el), i
+        for l in range(1, h):
+            for i in {0, 8 ** (h - 1 - l) - 1, rng.randrange(8 ** (h - 1 - l))}:
+                assert by[(l, i)] == P.hash_elems([by[(l - 1, 8 * i + j)] for j in range(8)]), (l, i)
+    finally:
+        p.close()
