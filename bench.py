@@ -13,13 +13,16 @@ A "step" is one MSM over one batch of synthetic scalars against the resident poi
   roofline  the dominant kernel (k_accumulate): algorithmic bytes / CUDA-event duration vs measured HBM peak
   cpu_baseline  the oracle's arkworks-0.3-style Pippenger ("port") on the box's host cores, bounded sample
 
-Multi-GPU (torchrun, one rank per GPU): the MSM is point-sharded (rank g owns points/scalars
-[g N/G, (g+1) N/G)), no data-path collective; the only exchange is an all-gather of the G 144-byte
-partial results, summed by bz_msm_combine_results.  scaling = "strong" (total work fixed at 2^26).
+Multi-GPU (torchrun, one rank per GPU): every rank opens a ranked DriverClient (bz_dclient_comm_init; torch.distributed
+only hands the NCCL id around).  The MSM is point-sharded (rank g owns points/scalars [g N/G, (g+1) N/G)); the library
+all-gathers the projective partial records with NCCL and sums them on its work stream, so result() is the full sum on every
+rank.  scaling = "strong" (total work fixed at 2^26).
 
-Secondary sections of the same JSON line (N = 1 only unless noted): `ntt` (2^27 NTT ms, device-resident; also at
-N > 1 as the four-step across the ranks; `ntt.e2e` = through the client calls with pinned host buffers), `dma_mode`
-(BASELINE.json configs[2]: BN254 2^24 with points AND scalars streamed from host memory every call).
+Other sections of the same JSON line, each VERIFIED inside the run: `config5` (N > 1: BLS12-377 2^26 across the GPUs,
+BASELINE.json configs[4]), `ntt` (2^27 NTT ms, device-resident; N > 1: four-step across the ranks; outputs checked against
+their definition at spot positions; `ntt.e2e` = through the client calls with pinned host buffers), `dma_mode` (configs[2]:
+BN254 2^24 with points AND scalars streamed from host memory every call), `precompute_x8` (the reference's x8 precomputed wire
+format in HBM mode), `poseidon` (TreeC tree of height 7), `config.plain_table_value` (no window-merged table).
 
 `--impl reference` times the reference's CPU definition of the path (the oracle port: the reference
 itself is Rust + an FPGA bitstream and cannot run here) on the host cores, same metric and config.
@@ -719,7 +722,8 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
-    affinity = bind_to_gpu_numa_node(local)
+    all_cpus = os.sched_getaffinity(0)
+    affinity = bind_to_gpu_numa_node(local) if world > 1 else "not bound (single GPU)"
     torch.cuda.set_device(local)
     dist = None
     dc = bz.DriverClient(str(local), bz.DriverConfig.driver_client_cfg(bz.CardType.B200))
@@ -857,6 +861,7 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             from oracle import capi
             capi.build()
+            os.sched_setaffinity(0, all_cpus)     # the CPU arm gets every host core the process started with
             ln = min(CPU_SAMPLE_LOG_N, args.log_n) if args.cpu_sample_log_n is None else args.cpu_sample_log_n
             cpu_port_rate(14)
             rr, th, dt = cpu_port_rate(ln)
