@@ -749,8 +749,18 @@ static int32_t collect(bz_msm* m, MsmTaskResult& r) {
 int32_t bz::leaf_wait_result(bz_msm* m) {
   int32_t rc = dc_select(m->dc);
   if (rc) return rc;
+  cudaEvent_t ev;
+  {
+    std::lock_guard<std::mutex> lk(m->mu);
+    if (m->results.empty()) return fail(BZ_ERR_NO_RESULT, "no task in flight (the reference would spin forever on RESULT_VALID)");
+    MsmTaskResult& r = m->results.front();
+    if (r.collected) return collect(m, r);
+    ev = r.done;
+  }
+  // block WITHOUT the client lock: a producer thread may keep queueing tasks (set_data / start_process) meanwhile
+  CUDA_TRY(BZ_ERR_READ, cudaEventSynchronize(ev));
   std::lock_guard<std::mutex> lk(m->mu);
-  if (m->results.empty()) return fail(BZ_ERR_NO_RESULT, "no task in flight (the reference would spin forever on RESULT_VALID)");
+  if (m->results.empty() || m->results.front().done != ev) return BZ_OK;   // another thread has already popped it
   return collect(m, m->results.front());
 }
 

@@ -561,3 +561,49 @@ def test_batched_affine_merged_table_2p20_matches_xyzz(dclient, oracle):
         assert res[0][1]["accumulate"] == "xyzz" and res[2][1]["accumulate"] == "batched-affine"
     finally:
         m.close()
+
+
+def test_producer_consumer_threads(dclient, oracle):
+    """One thread queues tasks (start_process + set_data), another drains them (wait_result + result), like the
+    reference's two-thread Poseidon test (integration_poseidon.rs:60-121): wait_result must not hold the client while it blocks."""
+    import threading
+    c = CURVE_BY_NAME["BLS12_381"]
+    n = 1 << 15
+    p0, q = seed_points(c, 8)
+    m = MSMClient.new(MSMInit(PointMemoryType.HBM, False, Curve.BLS381), dclient)
+    try:
+        m.generate_chain_points(p0 + q, 0, n, 0x50_0000_0000, 0)
+        params = MSMParams(n, (0x50_0000_0000, 0))
+        m.initialize(params)
+        K = 10
+        scs = [random_scalars(c, n, seed=700 + i) for i in range(K)]
+        exp = [oracle.chain_expected("BLS12_381", p0, q, s, n) for s in scs]
+        got, errors = [], []
+        queued = threading.Semaphore(0)
+
+        def producer():
+            try:
+                for s in scs:
+                    m.start_process()
+                    m.set_data(MSMInput(None, s, params))
+                    queued.release()
+            except Exception as e:      # pragma: no cover
+                errors.append(e)
+                queued.release()
+
+        def consumer():
+            try:
+                for _ in range(K):
+                    queued.acquire()
+                    m.wait_result()
+                    got.append(m.result())
+            except Exception as e:      # pragma: no cover
+                errors.append(e)
+
+        tp, tc = threading.Thread(target=producer), threading.Thread(target=consumer)
+        tp.start(); tc.start(); tp.join(120); tc.join(120)
+        assert not errors, errors
+        assert [r.result_label for r in got] == list(range(K))
+        assert [r.result for r in got] == exp
+    finally:
+        m.close()
