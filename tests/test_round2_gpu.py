@@ -607,3 +607,29 @@ def test_producer_consumer_threads(dclient, oracle):
         assert [r.result for r in got] == exp
     finally:
         m.close()
+
+
+def test_config5_size_bls12_377_2p26_one_gpu(dclient, oracle):
+    """The reference's 2^26 "max" size on BLS12-377 (integration_msm.rs:386-468 msm_bls12_377_max_test; BASELINE.json
+    configs[4] runs it across 8 GPUs, bench.py `config5`): HBM-resident points, two tasks (the second on the window-merged
+    table), bit-exact against the closed form of the chain workload."""
+    c = CURVE_BY_NAME["BLS12_377"]
+    n = 1 << 26
+    p0, q = seed_points(c, 377)
+    m = MSMClient.new(MSMInit(PointMemoryType.HBM, False, Curve.BLS377), dclient)
+    try:
+        base = 0x60_0000_0000
+        m.generate_chain_points(p0 + q, 0, n, base, 0)
+        params = MSMParams(n, (base, 0))
+        sc = random_scalars(c, n, seed=378)
+        exp = oracle.chain_expected("BLS12_377", p0, q, sc, n)
+        for it in range(2):
+            m.initialize(params)
+            m.start_process()
+            m.set_data(MSMInput(None, sc, params))
+            m.wait_result()
+            r = m.result()
+            assert r.result == exp and r.result_label == it
+        assert m.plan_info()["merged_table"] and m.plan_info()["windows"] == 11
+    finally:
+        m.close()
