@@ -806,6 +806,13 @@ def main():
                     break
                 except Exception:
                     traffic = None
+        # the HBM-bound part of the sweep -- scalar windowing + bucket sort (k_digits, two partition levels, final level):
+        # algorithmic bytes as implemented: digits 32 + 4 W per scalar; partition level 1 reads the 4-byte digit
+        # entry twice (histogram, scatter) and writes an 8-byte pair; level 2 reads the pair twice and writes it; the final
+        # level reads it twice and writes the 4-byte reference
+        entries = per * W
+        sort_bytes = per * (32 + 4 * W) + entries * ((4 + 4 + 8) + (8 + 8 + 8) + (8 + 8 + 4))
+        sort_gbs = sort_bytes / (r["sort_ms"] / 1e3) / 1e9
         line = {
             "metric": METRIC.replace("BLS12-381", cname.replace("_", "-")).replace("2^26", "2^%d" % args.log_n),
             "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -848,6 +855,10 @@ def main():
                          "note": "the sweep is integer-multiplier bound, not HBM bound (ncu: profiles/r2_ncu_accumulate*.txt); "
                                  "its HBM fraction is small by construction"},
         }
+        line["roofline_bucket_sort"] = {
+            "bound": "hbm", "kernels": "k_digits + k_part_hist/scan/scatter x2 + k_final (windowing and bucket sort of the sweep)",
+            "achieved": sort_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": sort_gbs / hbm_peak, "algorithmic_bytes": sort_bytes,
+            "ms": r["sort_ms"], "note": "the memory-bound phase of the sweep (5 % of the step); the EC-addition phase above is multiplier-bound"}
         if config5 is not None:
             line["config5"] = config5
         if ntt is not None:
