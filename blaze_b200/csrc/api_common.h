@@ -1,4 +1,4 @@
-// Helpers shared by the C-ABI translation units (c_api.cu, ntt_api.cu, poseidon_api.cu).
+// Helpers shared by the C-ABI translation units (dclient.cu, msm_client.cu, msm_api.cu, ntt_api.cu, poseidon_api.cu).
 #pragma once
 #include <cuda_runtime.h>
 

@@ -35,7 +35,7 @@ namespace bz {
 // digits.  Signed-digit recoding without a carry chain: s' = s + K with
 // K = sum_{w < W-1} 2^(c-1) * 2^(c w); digit_w = field_w(s') - 2^(c-1) for w < W-1 and the top
 // window takes the remaining bits unsigned.  Host code picks W so that the top digit of the
-// largest legal scalar is <= 2^(c-1) (c_api.cu: plan_windows).
+// largest legal scalar is <= 2^(c-1) (msm_client.cu: plan_windows).
 __global__ void __launch_bounds__(256) k_digits(const uint32_t* __restrict__ scalars, int words_per_scalar, uint64_t M,
                                                 int W, int c, DigitConst dc, uint32_t* __restrict__ dig,
                                                 int* __restrict__ err) {

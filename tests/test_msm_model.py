@@ -1,5 +1,5 @@
 """CPU: integer models of the MSM bookkeeping that the CUDA kernels implement (blaze_b200/csrc/msm_sort.cu,
-msm_curve.cuh, c_api.cu) -- the group is replaced by the integers, so every identity the kernels rely on can be
+msm_curve.cuh, msm_client.cu) -- the group is replaced by the integers, so every identity the kernels rely on can be
 checked exactly without a GPU:
   * signed-digit recoding (k_digits): sum_w d_w 2^(c w) == s, |d_w| <= 2^(c-1), top digit unsigned;
   * sort key / bucket slot permutation (sort_key, k_final, k_reduce_level's slot()): a bijection, partition levels
@@ -15,7 +15,7 @@ from oracle.py import curves
 
 
 def plan_windows(smax, sbits, c):
-    """c_api.cu plan_windows: smallest W >= ceil(sbits / c) whose top digit of the largest scalar is <= 2^(c-1)."""
+    """msm_client.cu plan_windows: smallest W >= ceil(sbits / c) whose top digit of the largest scalar is <= 2^(c-1)."""
     W = max(1, (sbits + c - 1) // c)
     while True:
         K = sum(1 << (c - 1 + c * w) for w in range(W - 1))
@@ -52,7 +52,7 @@ def test_signed_digits_recompose(name, c):
 
 
 def sort_levels(kb, Ms):
-    """c_api.cu make_plan: bits of the partition levels (rest) and of the final in-CTA level (fb)."""
+    """msm_client.cu make_plan: bits of the partition levels (rest) and of the final in-CTA level (fb)."""
     rest_t = 0
     while rest_t < 30 and Ms / (1 << rest_t) > 8192.0:
         rest_t += 1
