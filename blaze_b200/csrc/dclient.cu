@@ -277,7 +277,11 @@ const Nccl& nccl() {
     // a process that already carries NCCL (e.g. under torch.distributed) gets that copy; otherwise the system one
     void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
     if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
-    if (!h) { g_nccl.why = dlerror() ? dlerror() : "libnccl.so.2 not found"; return; }
+    if (!h) {
+      const char* why = dlerror();   // one call: dlerror() clears the message it returns
+      g_nccl.why = why ? why : "libnccl.so.2 not found";
+      return;
+    }
     auto sym = [&](const char* n) { return dlsym(h, n); };
     g_nccl.getUniqueId = reinterpret_cast<decltype(g_nccl.getUniqueId)>(sym("ncclGetUniqueId"));
     g_nccl.commInitRank = reinterpret_cast<decltype(g_nccl.commInitRank)>(sym("ncclCommInitRank"));
@@ -365,20 +369,20 @@ extern "C" int32_t bz_dclient_free(bz_dclient* dc) {
 
 extern "C" int32_t bz_dclient_reset(bz_dclient* dc) {
   // The reference toggles the DFX decoupler (dclient.rs:88-93): user logic is reset, HBM contents survive.
-  // Here: drain the work stream(s); the address space keeps its bytes.
+  // Here: drain the device(s) -- work streams and the clients' copy / tail streams; the address space keeps its bytes.
   if (!dc) return bz_fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null DriverClient");
   for (int g = dc_members(dc) - 1; g >= 0; g--) {
     bz_dclient* k = dc_member(dc, g);
     int32_t rc = dc_select(k);
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(k->mu);
-    CUDA_TRY(BZ_ERR_UNKNOWN, cudaStreamSynchronize(k->stream));
+    CUDA_TRY(BZ_ERR_UNKNOWN, cudaDeviceSynchronize());
   }
   return BZ_OK;
 }
 
 // dma_write / dma_read on a multi-device client address the FIRST device's HBM (an MSMClient on such a client shards
-// its own point set over the members through load_data_to_hbm, see msm_group.cu).
+// its own point set over the members through load_data_to_hbm, see msm_api.cu).
 extern "C" int32_t bz_dclient_dma_write(bz_dclient* dc, uint64_t base, uint64_t offset, const uint8_t* data, size_t len) {
   int32_t rc = dc_select(dc);
   if (rc) return rc;

@@ -211,7 +211,8 @@ struct ff {
       return add(mul(a, b), mul(c, d));
     } else {
 #if defined(BZ_NOINLINE_MUL) && defined(__CUDACC__)
-      return mul2_call(a, b, c, d);
+      if constexpr (kSplit) return mul2_split(a, b, c, d);
+      else return mul2_call(a, b, c, d);
 #else
       return mul2_sel(a, b, c, d);
 #endif
@@ -378,20 +379,154 @@ struct ff {
     return redc(T);
   }
 
+  // T[0..2N) = a^2 without reduction: N(N+1)/2 partial products.  Row i adds a_i * V_i with V_i as in the dedicated
+  // squaring below (diagonal term once, the limbs above i doubled through d = a << 1); limb i of T is final after
+  // row i.  Needs 2a < 2^(32N) (one spare bit: every field here).
+  template <int I>
+  BZ_HDI static void sqr_wide_rows(uint64_t* Ev, uint64_t* Ov, const uint32_t* a, const uint32_t* d, uint32_t* T) {
+    if constexpr (I < N) {
+      constexpr int NW = N / 2;
+      const uint32_t bi = a[I];
+      if constexpr (I == 0) {
+#pragma unroll
+        for (int k = 0; k < NW; k++) {
+          Ov[k] = cc::mul_wide(sq_limb(a, d, 0, 2 * k + 1), bi);
+          Ev[k] = cc::mul_wide(sq_limb(a, d, 0, 2 * k), bi);
+        }
+      } else {
+        uint64_t h = Ov[0] >> 32;
+        constexpr int K0 = I / 2;          // first odd-position product of this row: column 2 K0 + 1 >= I
+        constexpr int KE = (I + 1) / 2;    // first even-position product: column 2 KE >= I
+#pragma unroll
+        for (int k = 0; k < K0 && k < NW - 1; k++) Ov[k] = Ov[k + 1];
+        if constexpr (K0 < NW - 1) {
+          Ov[K0] = cc::add_cc64(Ov[K0 + 1], cc::mul_wide(sq_limb(a, d, I, 2 * K0 + 1), bi));
+#pragma unroll
+          for (int k = K0 + 1; k < NW - 1; k++)
+            Ov[k] = cc::addc_cc64(Ov[k + 1], cc::mul_wide(sq_limb(a, d, I, 2 * k + 1), bi));
+          Ov[NW - 1] = cc::addc64(0ull, cc::mul_wide(sq_limb(a, d, I, N - 1), bi));
+        } else {
+          Ov[NW - 1] = cc::mul_wide(sq_limb(a, d, I, N - 1), bi);
+        }
+        Ev[0] = cc::add_cc64(Ev[0], h);
+#pragma unroll
+        for (int k = 1; k < NW; k++)
+          Ev[k] = cc::addc_cc64(Ev[k], k >= KE ? cc::mul_wide(sq_limb(a, d, I, 2 * k), bi) : 0ull);
+        Ov[NW - 1] = cc::addc_hi32(Ov[NW - 1]);
+      }
+      T[I] = (uint32_t)Ev[0];
+      sqr_wide_rows<I + 1>(Ov, Ev, a, d, T);
+    }
+  }
+  BZ_HDI static void sqr_wide(const uint32_t* a, uint32_t* T) {
+    static_assert(F::BITS + 1 <= 32 * N, "doubled operand needs one spare bit");
+    constexpr int NW = N / 2;
+    uint64_t X[NW], Y[NW];
+    uint32_t d[N];
+    d[0] = a[0] << 1;
+#pragma unroll
+    for (int j = 1; j < N; j++) d[j] = (a[j] << 1) | (a[j - 1] >> 31);
+    sqr_wide_rows<0>(X, Y, a, d, T);
+    // N is even: the last row had Y in the even role; what is left is (Y >> 32) + X
+    T[N] = cc::add_cc((uint32_t)(Y[0] >> 32), (uint32_t)X[0]);
+#pragma unroll
+    for (int j = 1; j < N - 1; j++) {
+      uint32_t y = ((j + 1) & 1) ? (uint32_t)(Y[(j + 1) / 2] >> 32) : (uint32_t)Y[(j + 1) / 2];
+      uint32_t x = (j & 1) ? (uint32_t)(X[j / 2] >> 32) : (uint32_t)X[j / 2];
+      T[N + j] = cc::addc_cc(y, x);
+    }
+    T[2 * N - 1] = cc::addc((uint32_t)(X[NW - 1] >> 32), 0u);
+  }
+  BZ_HDI static E sqr_split(const E& a) {
+    uint32_t T[2 * N];
+    sqr_wide(a.v, T);
+    return redc(T);
+  }
+
+  // ---- BZ_SPLIT_MUL: product, squaring product and reduction as THREE shared routines ---------------------------
+  // mul = redc(prod), sqr = redc(sqr_wide), a*b + c*d = redc(prod + prod): the 2N-limb intermediate travels in
+  // registers through the call ABI (checked in SASS: no local memory).  The Karatsuba product above then costs
+  // 3/4 N^2 multiplier instructions where the interleaved routines spend N^2, and -- unlike BZ_KARATSUBA, which
+  // inlines product + reduction into each of mul / sqr / mul2 (31 KB) -- the three bodies together are ~11 KB:
+  // the accumulation loop stays inside the 32 KB instruction cache.
+  struct Wide {
+    uint32_t v[2 * N];
+  };
+#ifdef __CUDACC__
+  static __device__ __noinline__ Wide prodw_call(const E a, const E b) {
+    Wide t;
+    prod_kara(a.v, b.v, t.v);
+    return t;
+  }
+  static __device__ __noinline__ Wide sqrw_call(const E a) {
+    Wide t;
+    sqr_wide(a.v, t.v);
+    return t;
+  }
+  static __device__ __noinline__ E redc_call(const Wide t) { return redc(t.v); }
+#else
+  static Wide prodw_call(const E& a, const E& b) {
+    Wide t;
+    prod_kara(a.v, b.v, t.v);
+    return t;
+  }
+  static Wide sqrw_call(const E& a) {
+    Wide t;
+    sqr_wide(a.v, t.v);
+    return t;
+  }
+  static E redc_call(const Wide& t) { return redc(t.v); }
+#endif
+#if defined(__CUDACC__) && defined(BZ_SPLIT_NESTED)
+  // nested form: the product is inlined into the routine the caller sees, only the reduction is shared
+  static __device__ __noinline__ E mul_nested(const E a, const E b) {
+    Wide t;
+    prod_kara(a.v, b.v, t.v);
+    return redc_call(t);
+  }
+  static __device__ __noinline__ E sqr_nested(const E a) {
+    Wide t;
+    sqr_wide(a.v, t.v);
+    return redc_call(t);
+  }
+  BZ_HDI static E mul_split(const E& a, const E& b) { return mul_nested(a, b); }
+  BZ_HDI static E sqr_splitc(const E& a) { return sqr_nested(a); }
+#else
+  BZ_HDI static E mul_split(const E& a, const E& b) { return redc_call(prodw_call(a, b)); }
+  BZ_HDI static E sqr_splitc(const E& a) { return redc_call(sqrw_call(a)); }
+#endif
+  BZ_HDI static E mul2_split(const E& a, const E& b, const E& c, const E& d) {
+    static_assert(F::BITS + 2 <= 32 * N, "sum of two products needs two spare bits");
+    Wide t = prodw_call(a, b);
+    const Wide u = prodw_call(c, d);
+    t.v[0] = cc::add_cc(t.v[0], u.v[0]);
+#pragma unroll
+    for (int i = 1; i < 2 * N - 1; i++) t.v[i] = cc::addc_cc(t.v[i], u.v[i]);
+    t.v[2 * N - 1] = cc::addc(t.v[2 * N - 1], u.v[2 * N - 1]);
+    return redc_call(t);
+  }
+#if defined(BZ_SPLIT_MUL) && defined(__CUDACC__)
+  static constexpr bool kSplit = (N % 4 == 0) && (N >= BZ_SPLIT_MUL);
+#else
+  static constexpr bool kSplit = false;
+#endif
+
   // r = a*b/R mod p.  With BZ_NOINLINE_MUL the product and the square are real function calls (operands
   // and result travel in registers, ~35 MOVs per call): the unrolled bodies are 400 / 330 instructions, so
   // a mixed add with ten of them inlined is ~62 KB of code per loop iteration -- twice the SM's 32 KB
   // instruction cache (ncu: no_instruction stalls) -- while the called form keeps the loop under 24 KB.
   BZ_HDI static E mul(const E& a, const E& b) {
 #if defined(BZ_NOINLINE_MUL) && defined(__CUDACC__)
-    return mul_call(a, b);
+    if constexpr (kSplit) return mul_split(a, b);
+    else return mul_call(a, b);
 #else
     return mul_sel(a, b);
 #endif
   }
   BZ_HDI static E sqr(const E& a) {
 #if defined(BZ_NOINLINE_MUL) && defined(__CUDACC__)
-    return sqr_call(a);
+    if constexpr (kSplit) return sqr_splitc(a);
+    else return sqr_call(a);
 #else
     return sqr_inline(a);
 #endif

@@ -167,8 +167,9 @@ static int32_t group_after_launch(bz_msm* m) {
     bz_msm* p = m->parts[g];
     cudaSetDevice(p->dc->device);
     // behind the member's pipeline on the member's stream: its record travels device-to-device over NVLink
-    CUDA_TRY(BZ_ERR_UNKNOWN, cudaMemcpyPeerAsync(comb + (size_t)a * rs, m->dc->device, p->ws.result, p->dc->device, rs, p->dc->stream));
-    CUDA_TRY(BZ_ERR_UNKNOWN, cudaEventRecord(m->ev_part[g], p->dc->stream));
+    cudaStream_t pst = p->result_stream ? p->result_stream : p->dc->stream;   // the member's pipeline may end on its tail stream
+    CUDA_TRY(BZ_ERR_UNKNOWN, cudaMemcpyPeerAsync(comb + (size_t)a * rs, m->dc->device, p->ws.result, p->dc->device, rs, pst));
+    CUDA_TRY(BZ_ERR_UNKNOWN, cudaEventRecord(m->ev_part[g], pst));
     m->part_seen[g] = p->launched;
     a++;
   }

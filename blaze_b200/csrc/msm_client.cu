@@ -328,6 +328,18 @@ int32_t bz::leaf_new(bz_dclient* dc, int32_t curve, int32_t mem_type, int32_t is
   if (const char* e = getenv("BZ_MSM_PRECOMP")) { int v = atoi(e); if (v >= 0 && v <= 2) m->precomp_mode = v; }
   for (auto& slot : m->tev) for (auto& e : slot) cudaEventCreate(&e);
   cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking);
+  {
+    const char* e = getenv("BZ_MSM_TAIL");
+    if (!e || atoi(e) != 0) {
+      int lo = 0, hi = 0;
+      cudaDeviceGetStreamPriorityRange(&lo, &hi);   // hi = numerically lowest = greatest priority
+      if (cudaStreamCreateWithPriority(&m->tail, cudaStreamNonBlocking, hi) != cudaSuccess) { m->tail = nullptr; cudaGetLastError(); }
+      if (m->tail) {
+        cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&m->ev_tail_done, cudaEventDisableTiming);
+      }
+    }
+  }
   for (int b = 0; b < 2; b++) {
     cudaEventCreateWithFlags(&m->ev_copied[b], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&m->ev_consumed[b], cudaEventDisableTiming);
@@ -352,6 +364,7 @@ int32_t bz::leaf_free(bz_msm* m) {
   cudaSetDevice(m->dc->device);
   cudaStreamSynchronize(m->dc->stream);
   if (m->copy_stream) cudaStreamSynchronize(m->copy_stream);
+  if (m->tail) cudaStreamSynchronize(m->tail);
   for (auto& r : m->results) result_release(r);
   ws_free(m);
   if (m->table) cudaFree(m->table);
@@ -367,6 +380,9 @@ int32_t bz::leaf_free(bz_msm* m) {
   if (m->ev_points_copied) cudaEventDestroy(m->ev_points_copied);
   if (m->ev_points_consumed) cudaEventDestroy(m->ev_points_consumed);
   if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
+  if (m->tail) cudaStreamDestroy(m->tail);
+  if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+  if (m->ev_tail_done) cudaEventDestroy(m->ev_tail_done);
   if (m->pinned) cudaFreeHost(m->pinned);
   for (auto& slot : m->tev) for (auto& e : slot) if (e) cudaEventDestroy(e);
   for (auto& e : m->ev_part) if (e) cudaEventDestroy(e);
@@ -531,6 +547,9 @@ static int32_t launch_task(bz_msm* m) {
   if (m->stage_cur >= 0) CUDA_TRY(BZ_ERR_UNKNOWN, cudaStreamWaitEvent(st, m->ev_copied[m->stage_cur], 0));
   cudaEventRecord(ev[0], st);
   launch_msm_sort(m->plan, m->ws, m->scalars_src, st);
+  // the error word is final once the digits are extracted (k_digits is its only writer): read it back here, on the work
+  // stream, before the next task's memset can reach it -- the rest of this task may finish on the tail stream
+  CUDA_TRY(BZ_ERR_READ, cudaMemcpyAsync(r.host_err, m->ws.err, 4, cudaMemcpyDeviceToHost, st));
   if (m->stage_cur >= 0) {   // k_digits (the only reader of the staging buffer) is queued: mark it consumed
     cudaEventRecord(m->ev_consumed[m->stage_cur], st);
     m->consumed_valid[m->stage_cur] = true;
@@ -545,7 +564,13 @@ static int32_t launch_task(bz_msm* m) {
   }
   cudaEventRecord(ev[1], st);
   m->plan.raw_result = (m->raw_result || ranked) ? 1 : 0;
-  m->ops->bucket_phase(m->plan, m->ws, merged ? m->wtable : m->table, st);
+  m->ws.tail = m->tail;
+  m->ws.ev_fork = m->ev_fork;
+  m->ws.ev_tail_done = m->ev_tail_done;
+  m->ws.tail_busy = m->tail_busy ? 1 : 0;
+  const cudaStream_t work = st;
+  st = m->ops->bucket_phase(m->plan, m->ws, merged ? m->wtable : m->table, st);   // from here on: work or tail stream
+  m->result_stream = st;
   CUDA_TRY(BZ_ERR_UNKNOWN, cudaGetLastError());
   const uint8_t* final_rec = m->ws.result;
   if (ranked) {
@@ -560,8 +585,11 @@ static int32_t launch_task(bz_msm* m) {
   cudaEventRecord(ev[4], st);
   CUDA_TRY(BZ_ERR_UNKNOWN, cudaGetLastError());
   CUDA_TRY(BZ_ERR_READ, cudaMemcpyAsync(r.host_slot, final_rec, rs, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(BZ_ERR_READ, cudaMemcpyAsync(r.host_err, m->ws.err, 4, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(BZ_ERR_UNKNOWN, cudaEventRecord(r.done, st));
+  if (st != work) {
+    CUDA_TRY(BZ_ERR_UNKNOWN, cudaEventRecord(m->ev_tail_done, st));
+    m->tail_busy = true;
+  }
   nvtxRangePop();
   m->results.push_back(r);
   m->pending_tasks--;
@@ -805,6 +833,7 @@ int32_t bz::leaf_combine_results(bz_msm* m, const uint8_t* records, int32_t n, u
   std::lock_guard<std::mutex> lk(m->mu);
   rc = leaf_comb_reserve(m, rs * (n + 1));   // small scratch kept across calls (no cudaMalloc / cudaFree per step)
   if (rc) return rc;
+  if (m->tail) cudaStreamSynchronize(m->tail);   // a ranked task's tail uses the same scratch
   uint8_t* d = m->comb_dev;
   cudaStream_t st = m->dc->stream;
   cudaMemcpyAsync(d, records, rs * n, cudaMemcpyHostToDevice, st);

@@ -91,6 +91,11 @@ struct bz_msm {
   bool consumed_valid[2] = {false, false};
   int stage_next = 0, stage_cur = -1;
   const uint32_t* scalars_src = nullptr;   // where the pending task reads its scalars from
+  // tail stream (see MsmWorkspace::tail): higher priority than the work stream; BZ_MSM_TAIL=0 disables it
+  cudaStream_t tail = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_tail_done = nullptr;
+  bool tail_busy = false;
+  cudaStream_t result_stream = nullptr;   // stream on which the last launched task leaves ws.result (work or tail)
   uint8_t* pinned = nullptr;   // RESULT_SLOTS result slots
   // per result slot: start, sorted, accumulate begin, accumulate end, done -- a task's phase times are read from ITS
   // events, so two tasks in flight do not clobber each other's timers

@@ -732,7 +732,7 @@ struct CurveLaunch {
     k_points_to_mont<C><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(raw, (AffineT<C>*)table, n);
     g_kernel_launches += 1;
   }
-  static void bucket_phase(const MsmPlan& p, const MsmWorkspace& ws, const void* table, cudaStream_t st) {
+  static cudaStream_t bucket_phase(const MsmPlan& p, const MsmWorkspace& ws, const void* table, cudaStream_t st) {
     const uint32_t ngoff = (uint32_t)p.W * p.nb;
     XyzzM<C>* buckets = (XyzzM<C>*)ws.buckets;
     if (p.batch_affine != 1) cudaMemsetAsync(buckets, 0, (size_t)ngoff * sizeof(XyzzM<C>), st);
@@ -799,6 +799,8 @@ struct CurveLaunch {
     XyzzM<C>* scratch[2] = {(XyzzM<C>*)ws.red_a, (XyzzM<C>*)ws.red_b};
     int level = 0;
     const XyzzM<C>* top = nullptr;
+    // the previous task's tail (other stream) may still be reading the reduction scratch and ws.result
+    if (ws.tail && ws.tail_busy) cudaStreamWaitEvent(st, ws.ev_tail_done, 0);
     while (true) {
       const uint32_t s = level == 0 ? p.chunk : 4;
       int log_s = 0;
@@ -813,7 +815,7 @@ struct CurveLaunch {
         k_reduce_top<C><<<1, 256, 0, st>>>(A, Vin, n, a_stride, perm_bits, 1u << p.fb, s, p.W, level == 0 ? 1 : 0, scratch[0], scratch[1],
                                            level & 1, p.c, p.raw_result, ws.result);
         g_kernel_launches += 1;
-        return;
+        return st;
       }
       if (nt <= 8192)   // latency-bound level: four lanes per chunk (measured at 2^21 buckets: 32768 chunks are still
                         // throughput-bound -- 0.22 ms with one thread per chunk, 0.54 ms with four)
@@ -825,6 +827,13 @@ struct CurveLaunch {
       g_kernel_launches += 1;
       top = Vout;
       if (nch == 1) break;
+      if (level == 0 && ws.tail) {
+        // everything from here on is a few thousand additions on long dependency chains: continue on the tail stream
+        // (higher priority: its few CTAs are placed as soon as slots free up) and let the work stream start the next task
+        cudaEventRecord(ws.ev_fork, st);
+        cudaStreamWaitEvent(ws.tail, ws.ev_fork, 0);
+        st = ws.tail;
+      }
       A = Sout;
       Vin = Vout;
       n = nch;
@@ -834,6 +843,7 @@ struct CurveLaunch {
     }
     k_finish<C><<<1, 32, 0, st>>>(top, p.W, p.c, p.raw_result, ws.result);
     g_kernel_launches += 1;
+    return st;
   }
   static void build_wtable(void* wtable, uint64_t n, int levels, int c, cudaStream_t st) {
     constexpr int K = 16;

@@ -102,6 +102,13 @@ struct MsmWorkspace {
   void* ba_buf1;                  // affine lists of the odd rounds: (total/2 + W nb) entries
   void* ba2_scratch;              // batch_affine == 2: per-warp affine lists + running products
   cudaEvent_t ev_acc0, ev_acc1;   // bracket the accumulate kernel alone (roofline timing); may be null
+  // Side ("tail") stream for the latency-bound end of the pipeline -- the small levels of the running-sum reduction, the
+  // window combine, the final exchange and the result copy -- so that it overlaps the NEXT task's windowing / sort /
+  // accumulation instead of idling 140 SMs (set per task by the client; null = everything on the work stream).
+  cudaStream_t tail;
+  cudaEvent_t ev_fork;        // work stream: first reduction level done, the tail may start
+  cudaEvent_t ev_tail_done;   // tail stream: the previous task's tail has finished with the reduction scratch
+  int tail_busy;              // ev_tail_done has been recorded at least once
 };
 
 void launch_msm_sort(const MsmPlan& p, const MsmWorkspace& ws, const uint32_t* scalars_dev, cudaStream_t st);
@@ -116,7 +123,8 @@ struct CurveOps {
   size_t affine_list_bytes;   // packed affine point (batched-affine lists)
   size_t xyzz_bytes;
   void (*points_to_mont)(const uint8_t* raw, void* table, uint64_t n, cudaStream_t st);
-  void (*bucket_phase)(const MsmPlan& p, const MsmWorkspace& ws, const void* table, cudaStream_t st);
+  // returns the stream on which ws.result becomes ready: `st`, or ws.tail when the end of the pipeline was forked there
+  cudaStream_t (*bucket_phase)(const MsmPlan& p, const MsmWorkspace& ws, const void* table, cudaStream_t st);
   // window-merged table: level w (entries [w*n, (w+1)*n)) = 2^c * level w-1; level 0 must already be in place
   void (*build_wtable)(void* wtable, uint64_t n, int levels, int c, cudaStream_t st);
   // level-major table (entry w*n + i) -> wire records (levels affine points per base, canonical LE)

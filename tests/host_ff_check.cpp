@@ -42,6 +42,12 @@ static int field_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, in
       if constexpr (F::BITS + 2 <= 32 * F::N) r = ff<F>::mul2_kara(x, y, ff<F>::add(x, y), ff<F>::sub(x, y));
       else r = ff<F>::add(ff<F>::mul_kara(x, y), ff<F>::mul_kara(ff<F>::add(x, y), ff<F>::sub(x, y)));
       break;
+    case 13: r = ff<F>::sqr_split(x); break;              // squaring product + reduction-only Montgomery (BZ_SPLIT_MUL)
+    case 14: r = ff<F>::mul_split(x, y); break;           // redc(prod): the split-call product
+    case 15:
+      if constexpr (F::BITS + 2 <= 32 * F::N) r = ff<F>::mul2_split(x, y, ff<F>::add(x, y), ff<F>::sub(x, y));
+      else r = ff<F>::add(ff<F>::mul_split(x, y), ff<F>::mul_split(ff<F>::add(x, y), ff<F>::sub(x, y)));
+      break;
     default: return -1;
   }
   store<F>(out, r, nbytes);

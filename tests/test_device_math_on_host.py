@@ -45,6 +45,9 @@ def test_field_ops(hc, name):
             assert fop(hc, fid, 8, a, b, nb) == (a * b + (a + b) * (a - b)) % p
             assert fop(hc, fid, 9, a, b, nb) == a * b % p                               # Karatsuba + reduce-only
             assert fop(hc, fid, 10, a, b, nb) == (a * b + (a + b) * (a - b)) % p
+            assert fop(hc, fid, 13, a, b, nb) == a * a % p                              # split-call forms (BZ_SPLIT_MUL)
+            assert fop(hc, fid, 14, a, b, nb) == a * b % p
+            assert fop(hc, fid, 15, a, b, nb) == (a * b + (a + b) * (a - b)) % p
         for a in vals[1:10]:
             assert fop(hc, fid, 4, a, 0, nb) == pow(a, -1, p)
             assert fop(hc, fid, 12, a, 0, nb) == pow(a, -1, p)                        # Fermat ladder
