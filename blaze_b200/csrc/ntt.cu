@@ -162,8 +162,16 @@ __device__ __forceinline__ void dif_round(uint4* lo, uint4* hi, const uint4* trl
   }
 }
 
+// CTA shape: 256 threads x 2 CTAs per SM (122 registers).  Measured alternatives on B200 (scripts/ab_probe_ntt.sh):
+// see DESIGN.md 7b.
+#ifndef NTT_THREADS
+#define NTT_THREADS 256
+#endif
+#ifndef NTT_MINBLOCKS
+#define NTT_MINBLOCKS 2
+#endif
 template <class F>
-__global__ void __launch_bounds__(256, 2) k_ntt_pass(NttPassParams P) {
+__global__ void __launch_bounds__(NTT_THREADS, NTT_MINBLOCKS) k_ntt_pass(NttPassParams P) {
   typedef ff<F> A;
   typedef Fe<F> E;
   extern __shared__ uint4 smem[];
@@ -272,7 +280,7 @@ static cudaError_t launch_pass_t(const NttPassParams& Pin, cudaStream_t st) {
     if (e != cudaSuccess) return e;
   }
   uint64_t ctas = (P.Q + V - 1) / V;
-  k_ntt_pass<F><<<(unsigned)ctas, 256, smem, st>>>(P);
+  k_ntt_pass<F><<<(unsigned)ctas, NTT_THREADS, smem, st>>>(P);
   g_kernel_launches += 1;
   return cudaGetLastError();
 }

@@ -609,6 +609,43 @@ def test_producer_consumer_threads(dclient, oracle):
         m.close()
 
 
+def test_tail_stream_many_tasks_in_flight(dclient, oracle):
+    """Eight tasks queued back to back on one resident point set (window-merged table from the second on): the end of
+    every task -- upper reduction levels, window combine, result copy -- runs on the client's tail stream while the
+    next task's sort / accumulation already occupies the work stream.  Every task must return ITS sum, and the
+    non-canonical scalar of task 3 must be reported by task 3 only (the error word is read back before the next
+    task's windowing can clear it)."""
+    c = CURVE_BY_NAME["BLS12_381"]
+    n = 1 << 18
+    p0, q = seed_points(c, 81)
+    m = MSMClient.new(MSMInit(PointMemoryType.HBM, False, Curve.BLS381), dclient)
+    try:
+        m.generate_chain_points(p0 + q, 0, n, 0x60_0000_0000, 0)
+        params = MSMParams(n, (0x60_0000_0000, 0))
+        m.initialize(params)
+        K = 8
+        scs = [np.array(random_scalars(c, n, seed=900 + i), dtype=np.uint8, copy=True) for i in range(K)]
+        scs[3][32 * 77:32 * 78] = 0xff                      # >= r
+        exp = [oracle.chain_expected("BLS12_381", p0, q, s, n) if i != 3 else None for i, s in enumerate(scs)]
+        for s in scs:
+            m.start_process()
+            m.set_data(MSMInput(None, s, params))
+        for i in range(K):
+            if i == 3:
+                with pytest.raises(bz.error.InvalidPrimitiveParam):
+                    m.wait_result()
+                with pytest.raises(bz.error.InvalidPrimitiveParam):
+                    m.result()
+                continue
+            m.wait_result()
+            r = m.result()
+            assert r.result_label == i
+            assert r.result == exp[i], "task %d" % i
+        assert m.plan_info()["merged_table"]
+    finally:
+        m.close()
+
+
 def test_config5_size_bls12_377_2p26_one_gpu(dclient, oracle):
     """The reference's 2^26 "max" size on BLS12-377 (integration_msm.rs:386-468 msm_bls12_377_max_test; BASELINE.json
     configs[4] runs it across 8 GPUs, bench.py `config5`): HBM-resident points, two tasks (the second on the window-merged
