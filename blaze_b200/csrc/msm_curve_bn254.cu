@@ -1,6 +1,8 @@
 // Bn254 instantiation of the MSM back end (see msm_curve.cuh).
 // field products as real calls: keeps the hot loops inside the 32 KB instruction cache (measured: ff.cuh)
+#ifndef BZ_INLINE_MUL_TU
 #define BZ_NOINLINE_MUL 1
+#endif
 #include "msm_curve.cuh"
 #include "msm_ba.cuh"
 

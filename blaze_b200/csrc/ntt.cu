@@ -22,8 +22,14 @@
 //
 // Twiddles: w^e for any e < 2^log_root from two tables (w^x, x < 2^14; w^(x 2^14)) -- one extra
 // product -- built once per (log_root, direction) on the device from the field's 2-adic root.
-// field products as real calls: keeps the hot loops inside the 32 KB instruction cache (measured: ff.cuh)
+// Field products INLINED (111 KB of code for the pass kernel): for the 8-limb scalar fields the call marshalling of a
+// called product (16-24 IMAD.MOV on the multiplier pipe per 112 IMAD.WIDE) costs more than the instruction-cache misses
+// of the unrolled body -- measured on B200: 2^27 37.38 ms with calls, 35.73 ms inlined, 35.98 ms with only the butterflies'
+// internal or only the inter-round twiddle products inlined (profiles/r2_ntt_variants.txt).
+// The 12-limb base fields of the MSM are the other way round (ff.cuh).  -DNTT_CALL_MUL restores the called form.
+#ifdef NTT_CALL_MUL
 #define BZ_NOINLINE_MUL 1
+#endif
 #include <cuda_runtime.h>
 
 #include <cstdint>

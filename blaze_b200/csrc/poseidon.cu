@@ -10,7 +10,9 @@
 // Layout: constants in global memory in Montgomery form (every thread of a warp reads the same
 // address: one broadcast transaction per load); the state lives in registers (t x 8 limbs).
 // field products as real calls: keeps the hot loops inside the 32 KB instruction cache (measured: ff.cuh)
+#ifndef BZ_INLINE_MUL_TU
 #define BZ_NOINLINE_MUL 1
+#endif
 #include <cuda_runtime.h>
 
 #include <cstdint>
