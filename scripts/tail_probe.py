@@ -50,8 +50,25 @@ for logn in sizes:
             ok &= m.result().result == exp
         return ok
 
+    pinned = torch.frombuffer(bytearray(sc), dtype=torch.uint8).pin_memory()
+
+    def enqueue_host():
+        m.initialize(params)
+        m.start_process()
+        m.set_data(bz.MSMInput(None, (pinned.data_ptr(), n * 32), params))
+
+    def pipe_host(k):
+        ok = True
+        enqueue_host()
+        for i in range(k):
+            if i + 1 < k:
+                enqueue_host()
+            m.wait_result()
+            ok &= m.result().result == exp
+        return ok
+
     serial(4)
-    for name, fn in (("serial", serial), ("pipelined", pipe), ("serial", serial), ("pipelined", pipe)):
+    for name, fn in (("serial", serial), ("pipelined", pipe), ("pipe_host", pipe_host), ("pipelined", pipe), ("pipe_host", pipe_host)):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         ok = fn(K)
