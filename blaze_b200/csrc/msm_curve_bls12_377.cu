@@ -1,6 +1,6 @@
 // Bls12_377 instantiation of the MSM back end (see msm_curve.cuh).
 // field products as real calls: keeps the hot loops inside the 32 KB instruction cache (measured: ff.cuh)
-#ifndef BZ_INLINE_MUL_TU
+#ifndef BZ_INLINE_MUL_TU   // A/B switch (scripts/build_variant.sh): inlined products measured slower here, profiles/r2_inline_call_ab.txt
 #define BZ_NOINLINE_MUL 1
 #endif
 #include "msm_curve.cuh"

@@ -10,7 +10,7 @@
 // Layout: constants in global memory in Montgomery form (every thread of a warp reads the same
 // address: one broadcast transaction per load); the state lives in registers (t x 8 limbs).
 // field products as real calls: keeps the hot loops inside the 32 KB instruction cache (measured: ff.cuh)
-#ifndef BZ_INLINE_MUL_TU
+#ifndef BZ_INLINE_MUL_TU   // A/B switch (scripts/build_variant.sh): inlined products measured slower here, profiles/r2_inline_call_ab.txt
 #define BZ_NOINLINE_MUL 1
 #endif
 #include <cuda_runtime.h>
