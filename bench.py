@@ -4,8 +4,10 @@
 Metric (BASELINE.json): BLS12-381 MSM scalar-mults/sec at 2^26, HBM-resident points (configs[1]).
 A "step" is one MSM over one batch of synthetic scalars against the resident point set.
 
-  value   whole-job scalar-mults/s, device time (CUDA events on the library's launch stream), scalars
-          already resident in HBM when the timed region starts
+  value   whole-job scalar-mults/s: K steps bracketed by barrier + synchronize (max over ranks), scalars already
+          resident in HBM when the timed region starts, two tasks in flight through the client's task queue
+          (config.serial_value: every result awaited before the next task is queued); the per-phase device times
+          come from CUDA events the library records on its launch streams
   e2e     the same metric through the reference-facing call order
           (initialize -> start_process -> set_data(host scalars) -> wait_result -> result) with pinned HOST
           buffers: the H2D copy of the step's scalars and the D2H read of the result are inside the
@@ -15,7 +17,7 @@ A "step" is one MSM over one batch of synthetic scalars against the resident poi
 
 Multi-GPU (torchrun, one rank per GPU): every rank opens a ranked DriverClient (bz_dclient_comm_init; torch.distributed
 only hands the NCCL id around).  The MSM is point-sharded (rank g owns points/scalars [g N/G, (g+1) N/G)); the library
-all-gathers the projective partial records with NCCL and sums them on its work stream, so result() is the full sum on every
+all-gathers the projective partial records with NCCL and sums them on the device (its tail stream), so result() is the full sum on every
 rank.  scaling = "strong" (total work fixed at 2^26).
 
 Other sections of the same JSON line, each VERIFIED inside the run: `config5` (N > 1: BLS12-377 2^26 across the GPUs,
