@@ -190,7 +190,7 @@ extern "C" int32_t bz_ntt_set_data(bz_ntt* t, size_t buf_host, const uint8_t* da
   if (len != t->n * 32) return bz_fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "data length %zu != %llu*32", len, (unsigned long long)t->n);
   int32_t rc = dc_select(t->dc);
   if (rc) return rc;
-  std::lock_guard<std::mutex> lk(t->mu);
+  std::unique_lock<std::mutex> lk(t->mu);
   rc = ntt_alloc_slot(t, (int)buf_host);
   if (rc) return rc;
   // the slot must be idle: its last transform finished, its last result read out (stream-side waits only)
@@ -200,6 +200,9 @@ extern "C" int32_t bz_ntt_set_data(bz_ntt* t, size_t buf_host, const uint8_t* da
   CUDA_TRY(BZ_ERR_WRITE, cudaMemcpyAsync(t->buf[buf_host][t->cur[buf_host]], data, len, cudaMemcpyHostToDevice, st));
   CUDA_TRY(BZ_ERR_WRITE, cudaEventRecord(t->ev_in[buf_host], st));
   t->in_valid[buf_host] = true;
+  // The host blocks on the copy WITHOUT the client lock: another thread may queue result() of the other slot meanwhile
+  // (PCIe is full duplex: with a feeder and a drainer thread the two directions overlap, bench.py ntt.e2e.threaded_ms).
+  lk.unlock();
   CUDA_TRY(BZ_ERR_WRITE, cudaStreamSynchronize(st));   // caller may drop `data` (move-in semantics); the work stream keeps running
   return BZ_OK;
 }
@@ -284,9 +287,12 @@ extern "C" int32_t bz_ntt_wait_result(bz_ntt* t) {
   if (!t) return bz_fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "null NTTClient");
   int32_t rc = dc_select(t->dc);
   if (rc) return rc;
-  std::lock_guard<std::mutex> lk(t->mu);
+  std::unique_lock<std::mutex> lk(t->mu);
   if (!t->launched) return bz_fail(BZ_ERR_NO_RESULT, "no transform in flight");
-  CUDA_TRY(BZ_ERR_READ, cudaEventSynchronize(t->done));
+  cudaEvent_t done = t->done;
+  lk.unlock();   // block without the client lock (the reference busy-polls a register here): copies of the other slot go on
+  CUDA_TRY(BZ_ERR_READ, cudaEventSynchronize(done));
+  lk.lock();
   cudaEventElapsedTime(&t->last_ms, t->ev[0], t->ev[1]);
   if (t->err_host && *t->err_host)
     return bz_fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "the transformed vector held a non-canonical element (>= r); its output is undefined");
@@ -299,7 +305,7 @@ extern "C" int32_t bz_ntt_result(bz_ntt* t, size_t buf_num, uint8_t* out, size_t
   if (out_len < t->n * 32) return bz_fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "result buffer too small");
   int32_t rc = dc_select(t->dc);
   if (rc) return rc;
-  std::lock_guard<std::mutex> lk(t->mu);
+  std::unique_lock<std::mutex> lk(t->mu);
   rc = ntt_alloc_slot(t, (int)buf_num);
   if (rc) return rc;
   cudaStream_t st = t->d2h;
@@ -308,7 +314,8 @@ extern "C" int32_t bz_ntt_result(bz_ntt* t, size_t buf_num, uint8_t* out, size_t
   CUDA_TRY(BZ_ERR_READ, cudaMemcpyAsync(out, t->buf[buf_num][t->cur[buf_num]], t->n * 32, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(BZ_ERR_READ, cudaEventRecord(t->ev_out[buf_num], st));
   t->out_valid[buf_num] = true;
-  CUDA_TRY(BZ_ERR_READ, cudaStreamSynchronize(st));   // blocks the host on this copy only
+  lk.unlock();
+  CUDA_TRY(BZ_ERR_READ, cudaStreamSynchronize(st));   // blocks the host on this copy only, without the client lock
   return BZ_OK;
 }
 

@@ -126,6 +126,60 @@ def test_ntt_pipeline_reference_order_overlapped_copies(dclient, oracle):
         t.close()
 
 
+def test_ntt_feeder_and_drainer_threads(dclient, oracle):
+    """Three host threads on one NTTClient (the client is Send + Sync like the reference's): a feeder calls set_data, the
+    main thread start_process / wait_result, a drainer result.  The blocking calls do not hold the client lock, so the
+    copy into one slot and the read-out of the other overlap; a slot is refilled only after its previous result was read."""
+    import threading
+    name, log_n = "BLS12_381", 20
+    n = 1 << log_n
+    t = NTTClient.new_ex(dclient, FIELDS[name], log_n)
+    try:
+        rounds = 8
+        ins = [rand_elems(name, n, seed=900 + i) for i in range(rounds)]
+        exps = []
+        for d in ins:
+            e = d.copy()
+            oracle.ntt(name, e, log_n)
+            exps.append(bytes(e))
+        t.initialize(NttInit())
+        in_ready = [threading.Semaphore(0) for _ in range(rounds)]
+        cmp_done = [threading.Semaphore(0) for _ in range(rounds)]
+        out_done = [threading.Semaphore(0) for _ in range(rounds)]
+        outs, errs = [None] * rounds, []
+
+        def feeder():
+            try:
+                for i in range(rounds):
+                    if i >= 2:
+                        assert out_done[i - 2].acquire(timeout=60)
+                    t.set_data(NTTInput(i % 2, ins[i]))
+                    in_ready[i].release()
+            except Exception as ex:      # pragma: no cover
+                errs.append(ex)
+
+        def drainer():
+            try:
+                for i in range(rounds):
+                    assert cmp_done[i].acquire(timeout=60)
+                    outs[i] = bytes(t.result(i % 2))
+                    out_done[i].release()
+            except Exception as ex:      # pragma: no cover
+                errs.append(ex)
+        tf, td = threading.Thread(target=feeder), threading.Thread(target=drainer)
+        tf.start(); td.start()
+        for i in range(rounds):
+            assert in_ready[i].acquire(timeout=60)
+            t.start_process(i % 2)
+            t.wait_result()
+            cmp_done[i].release()
+        tf.join(120); td.join(120)
+        assert not errs, errs
+        assert outs == exps
+    finally:
+        t.close()
+
+
 def test_ntt_reference_constructor_is_2p27(dclient):
     t = NTTClient.new(NTT.Ntt, dclient)
     try:
