@@ -314,6 +314,9 @@ struct bz_poseidon {
   size_t pending_head = 0;
   uint32_t last_hash_id = 0;
   cudaEvent_t ev[2] = {nullptr, nullptr};
+  cudaEvent_t ev_layer[10][3] = {};  // per layer: hash begin, hash end, digests copied to the host
+  uint8_t* stage_host = nullptr;    // pinned staging of one flush's digests
+  size_t stage_cap = 0;
   double device_ms = 0;             // kernel time since initialize (CUDA events around every hash launch)
   std::mutex mu;
 };
@@ -344,6 +347,7 @@ extern "C" int32_t bz_poseidon_new(bz_dclient* dc, int32_t hash_type, bz_poseido
   p->dc = dc;
   cudaEventCreate(&p->ev[0]);
   cudaEventCreate(&p->ev[1]);
+  for (auto& l : p->ev_layer) for (auto& e : l) cudaEventCreate(&e);
   *out = p;
   return BZ_OK;
 }
@@ -363,6 +367,8 @@ extern "C" int32_t bz_poseidon_free(bz_poseidon* p) {
   free_tree(p);
   for (auto& w : p->par) for (auto& q : w) if (q.consts) cudaFree(q.consts);
   for (auto& e : p->ev) if (e) cudaEventDestroy(e);
+  for (auto& l : p->ev_layer) for (auto& e : l) if (e) cudaEventDestroy(e);
+  if (p->stage_host) cudaFreeHost(p->stage_host);
   delete p;
   return BZ_OK;
 }
@@ -424,37 +430,60 @@ static int32_t flush(bz_poseidon* p) {
     p->elems_on_device += p->staged.size() / 32;
     p->staged.clear();
   }
-  std::vector<uint8_t> host;
+  // Every layer that has new complete nodes is hashed now.  The launches go out back to back (layer l reads what layer
+  // l-1 wrote: stream order), each followed by the copy of its digests into pinned staging; the host then builds the
+  // 64-byte records of layer l as soon as ITS copy has landed, i.e. while the layers above are still being hashed.
+  struct Batch { uint32_t l; uint64_t first, n; size_t stage_off; };
+  std::vector<Batch> batches;
+  uint64_t avail_prev = 0;
+  size_t stage_need = 0;
   for (uint32_t l = 0; l < p->height; l++) {
-    uint64_t avail = l == 0 ? p->elems_on_device / p->in_arity : p->done[l - 1] / 8;
+    const uint64_t avail = l == 0 ? p->elems_on_device / p->in_arity : avail_prev / 8;
+    avail_prev = avail;
     if (avail <= p->done[l]) break;
-    uint64_t n = avail - p->done[l];
+    batches.push_back({l, p->done[l], avail - p->done[l], stage_need});
+    stage_need += (size_t)(avail - p->done[l]) * 32;
+  }
+  if (batches.empty()) return BZ_OK;
+  if (p->stage_cap < stage_need) {
+    if (p->stage_host) cudaFreeHost(p->stage_host);
+    p->stage_host = nullptr;
+    p->stage_cap = 0;
+    CUDA_TRY(BZ_ERR_READ, cudaHostAlloc((void**)&p->stage_host, stage_need, cudaHostAllocDefault));
+    p->stage_cap = stage_need;
+  }
+  for (size_t b = 0; b < batches.size(); b++) {
+    const Batch& B = batches[b];
+    const uint32_t l = B.l;
     int t = (l == 0 && p->in_arity == 11) ? 12 : 9;
     const PoseidonParams& q = p->par[width_index(t)][0];
-    const uint8_t* in = l == 0 ? p->d_inputs + p->done[0] * (uint64_t)p->in_arity * 32 : p->d_layer[l - 1] + p->done[l] * 8 * 32;
-    uint8_t* out = p->d_layer[l] + p->done[l] * 32;
-    cudaEventRecord(p->ev[0], st);
-    poseidon_hash(t, (const uint4*)in, n, q.consts, P_RF, P_RP, 0, (uint4*)out, st);
-    cudaEventRecord(p->ev[1], st);
+    const uint8_t* in = l == 0 ? p->d_inputs + B.first * (uint64_t)p->in_arity * 32 : p->d_layer[l - 1] + B.first * 8 * 32;
+    uint8_t* out = p->d_layer[l] + B.first * 32;
+    cudaEventRecord(p->ev_layer[l][0], st);
+    poseidon_hash(t, (const uint4*)in, B.n, q.consts, P_RF, P_RP, 0, (uint4*)out, st);
+    cudaEventRecord(p->ev_layer[l][1], st);
     CUDA_TRY(BZ_ERR_UNKNOWN, cudaGetLastError());
-    host.resize(n * 32);
-    CUDA_TRY(BZ_ERR_READ, cudaMemcpyAsync(host.data(), out, n * 32, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(BZ_ERR_READ, cudaStreamSynchronize(st));
+    CUDA_TRY(BZ_ERR_READ, cudaMemcpyAsync(p->stage_host + B.stage_off, out, B.n * 32, cudaMemcpyDeviceToHost, st));
+    cudaEventRecord(p->ev_layer[l][2], st);
+  }
+  if (p->pending_head && p->pending_head * 64 == p->pending.size()) { p->pending.clear(); p->pending_head = 0; }
+  for (const Batch& B : batches) {
+    CUDA_TRY(BZ_ERR_READ, cudaEventSynchronize(p->ev_layer[B.l][2]));
     float ms = 0;
-    cudaEventElapsedTime(&ms, p->ev[0], p->ev[1]);
+    cudaEventElapsedTime(&ms, p->ev_layer[B.l][0], p->ev_layer[B.l][1]);
     p->device_ms += ms;
-    if (p->pending_head && p->pending_head * 64 == p->pending.size()) { p->pending.clear(); p->pending_head = 0; }
     const size_t at = p->pending.size();
-    p->pending.resize(at + n * 64);
-    for (uint64_t i = 0; i < n; i++) {
+    p->pending.resize(at + B.n * 64);
+    const uint8_t* src = p->stage_host + B.stage_off;
+    for (uint64_t i = 0; i < B.n; i++) {
       uint8_t* rec = &p->pending[at + i * 64];
-      memcpy(rec, &host[i * 32], 32);
+      memcpy(rec, src + i * 32, 32);
       memset(rec + 32, 0, 32);
-      uint64_t id = p->done[l] + i;
-      uint64_t meta = (id & 0x3fffffffull) | ((uint64_t)l << 30);   // poseidon_api.rs:50-61
+      uint64_t id = B.first + i;
+      uint64_t meta = (id & 0x3fffffffull) | ((uint64_t)B.l << 30);   // poseidon_api.rs:50-61
       memcpy(rec + 32, &meta, 8);
     }
-    p->done[l] = avail;
+    p->done[B.l] = B.first + B.n;
   }
   // tree complete: the next element starts a new tree
   if (p->done[p->height - 1] == 1) {
