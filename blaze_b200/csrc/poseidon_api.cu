@@ -313,7 +313,6 @@ struct bz_poseidon {
   std::vector<uint8_t> pending;     // 64-byte records, FIFO: [pending_head, pending.size() / 64)
   size_t pending_head = 0;
   uint32_t last_hash_id = 0;
-  cudaEvent_t ev[2] = {nullptr, nullptr};
   cudaEvent_t ev_layer[10][3] = {};  // per layer: hash begin, hash end, digests copied to the host
   uint8_t* stage_host = nullptr;    // pinned staging of one flush's digests
   size_t stage_cap = 0;
@@ -345,8 +344,6 @@ extern "C" int32_t bz_poseidon_new(bz_dclient* dc, int32_t hash_type, bz_poseido
   if (hash_type != 0) return bz_fail(BZ_ERR_INVALID_PRIMITIVE_PARAM, "unknown hash type %d", hash_type);
   bz_poseidon* p = new bz_poseidon();
   p->dc = dc;
-  cudaEventCreate(&p->ev[0]);
-  cudaEventCreate(&p->ev[1]);
   for (auto& l : p->ev_layer) for (auto& e : l) cudaEventCreate(&e);
   *out = p;
   return BZ_OK;
@@ -366,7 +363,6 @@ extern "C" int32_t bz_poseidon_free(bz_poseidon* p) {
   cudaStreamSynchronize(dc_stream(p->dc));
   free_tree(p);
   for (auto& w : p->par) for (auto& q : w) if (q.consts) cudaFree(q.consts);
-  for (auto& e : p->ev) if (e) cudaEventDestroy(e);
   for (auto& l : p->ev_layer) for (auto& e : l) if (e) cudaEventDestroy(e);
   if (p->stage_host) cudaFreeHost(p->stage_host);
   delete p;
