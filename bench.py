@@ -277,42 +277,47 @@ def ntt_section(args, bz, torch, dist, dc, rank, world, local):
             out_done = [threading.Semaphore(0) for _ in range(kt)]
             errs = []
 
+            WAIT = 120   # seconds: a failed thread must not leave the others waiting for ever
+
+            def take(sem):
+                if errs or not sem.acquire(timeout=WAIT):
+                    raise RuntimeError("threaded NTT cycle: a peer thread failed or timed out")
+
             def feeder():
                 try:
                     for i in range(kt):
                         if i >= 2:
-                            out_done[i - 2].acquire()
+                            take(out_done[i - 2])
                         t.set_data(bz.NTTInput(i % 2, bi))
                         in_ready[i].release()
                 except Exception as ex:      # pragma: no cover
                     errs.append(ex)
-                    for sem in in_ready:
-                        sem.release()
 
             def drainer():
                 try:
                     for i in range(kt):
-                        cmp_done[i].acquire()
+                        take(cmp_done[i])
                         t.result(i % 2, out=outs[i % 2])
                         out_done[i].release()
                 except Exception as ex:      # pragma: no cover
                     errs.append(ex)
-                    for sem in out_done:
-                        sem.release()
             torch.cuda.synchronize()
-            tf, td = threading.Thread(target=feeder), threading.Thread(target=drainer)
+            tf, td = threading.Thread(target=feeder, daemon=True), threading.Thread(target=drainer, daemon=True)
             t0 = time.perf_counter()
             tf.start()
             td.start()
-            for i in range(kt):
-                in_ready[i].acquire()
-                if errs:
-                    break
-                t.start_process(i % 2)
-                t.wait_result()
-                cmp_done[i].release()
-            tf.join()
-            td.join()
+            try:
+                for i in range(kt):
+                    take(in_ready[i])
+                    t.start_process(i % 2)
+                    t.wait_result()
+                    cmp_done[i].release()
+            except Exception as ex:      # pragma: no cover
+                errs.append(ex)
+            for sem in in_ready + cmp_done + out_done:   # whatever happened: nobody stays blocked
+                sem.release()
+            tf.join(WAIT)
+            td.join(WAIT)
             torch.cuda.synchronize()
             thr_ms = 1e3 * (time.perf_counter() - t0) / kt
             thr_ok = (not errs) and bool(torch.equal(hout, hout2))       # same input in both slots: same transform out
